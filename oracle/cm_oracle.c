@@ -1,0 +1,44 @@
+/*
+ * cm_oracle.c -- CPU oracle for the contrast-maximization hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see cm_oracle_impl.h).  Builds the fp32 oracle
+ * (operation-for-operation restatement of the reference's eager CPU path)
+ * and an fp64 twin of the same algorithm used for triangulation.
+ *
+ * Parity pin: the reference ships no tests or golden vectors (SURVEY.md §4,
+ * §8c); this oracle is pinned against the reference itself, imported live in
+ * the build container, by tests/test_oracle_vs_reference.py and through the
+ * committed vectors under tests/golden/ (made by tests/golden/make_golden.py).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "cm_oracle.h"
+
+#define REAL float
+#define FN(n) n##_f32
+#define R_FMA fmaf
+#define R_FLOOR floorf
+#define R_FABS fabsf
+#define R_RINT rintf
+#include "cm_oracle_impl.h"
+#undef REAL
+#undef FN
+#undef R_FMA
+#undef R_FLOOR
+#undef R_FABS
+#undef R_RINT
+
+#define REAL double
+#define FN(n) n##_f64
+#define R_FMA fma
+#define R_FLOOR floor
+#define R_FABS fabs
+#define R_RINT rint
+#include "cm_oracle_impl.h"
+
+int orc_num_slots(const orc_cfg *c, int linear)
+{
+    return linear ? linear_slots_f32(c, NULL) : build_slots_f32(c, NULL);
+}
+int orc_version(void) { return 1; }
