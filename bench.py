@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the contrast-maximization hot path (BASELINE.json: "CM loss fwd+bwd Mevents/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One step = one full loss window through the reference-facing API of
+taming_event_flow_b200.loss.flow: `update` x P passes -> `forward` -> `backward` (flow gradients
+delivered to every flow map).  Mevents/s = input events of the window (each counted once,
+with-gradient + detached) / step time.
+
+* `value`   inputs already resident in HBM when the timed region starts (a fresh device copy of the
+            event tensors per step, because `update` mutates the caller's timestamps in place).
+* `e2e`     same metric with every input (events, masks, flow maps) in pinned HOST memory and the
+            loss + flow gradients read back to the host, all copies inside the timed region.
+* `roofline` for the dominant kernel, timed live with CUDA events on the launching stream
+            (library-side ProfScope), against MEASURED_PEAKS.json.
+* `cpu_baseline` the CPU oracle (oracle/, an OpenMP C port of the reference algorithm) on a bounded
+            sample of the same workload, on the host cores of this box.
+* `--impl reference` times that CPU port alone (the reference itself is Python/PyTorch and cannot
+            travel to the GPU box).
+
+Multi-GPU (torchrun): the batch of independent event-window sequences is sharded, one process per GPU,
+no data-path collective (the loss sums over independent samples) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: B, P, N, Nd, H, W, F, S, mode, sigma, distribution, warping
+    # north_star target: 1M-event 480x640 windows (BASELINE.json configs[4] at 1M events/window)
+    "iterative_480x640_1Mev": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "iterative_480x640_100kev": dict(B=1, P=10, N=100_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "iterative_480x640_4Mev": dict(B=1, P=10, N=4_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "iterative_480x640_1Mev_edges": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="edges", warping="Iterative"),
+    # BASELINE.json configs[0]: 128x128 crops, batch 8, 10 passes x (10k grad + 10k detached)
+    "iterative_128x128_b8_f1": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "iterative_128x128_b8_f4": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "linear_128x128_b8_f4": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Linear"),
+    "linear_480x640_1Mev": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Linear"),
+}
+DEFAULT_WORKLOAD = "iterative_480x640_1Mev"
+
+
+def fast_sequence(seed, wl, device="cpu", n_override=None):
+    """Synthetic loss window with the statistics of taming_event_flow_b200.synthetic.make_sequence, vectorised
+    over the batch so that 10M events are generated in seconds."""
+    from taming_event_flow_b200 import synthetic as syn
+
+    B, P, H, W, F = wl["B"], wl["P"], wl["H"], wl["W"], wl["F"]
+    N = wl["N"] if n_override is None else n_override
+    Nd = wl["Nd"] if n_override is None else (n_override if wl["Nd"] > 0 else 0)
+    gen = torch.Generator().manual_seed(seed)
+    seq = {"flows": [], "events": [], "masks": [], "d_events": [], "d_masks": []}
+
+    def window(n, t):
+        if wl["dist"] != "uniform":
+            return syn.make_window(gen, B, n, H, W, False, wl["dist"], t)
+        ev = torch.zeros(B, n, 4)
+        if n > 0:
+            ts, _ = torch.sort(torch.rand(B, n, generator=gen), dim=1)
+            if n > 1:
+                ts = (ts - ts[:, :1]) / (ts[:, -1:] - ts[:, :1])
+            else:
+                ts = torch.zeros(B, n)
+            ev[:, :, 0] = ts
+            ev[:, :, 1] = torch.randint(0, H, (B, n), generator=gen).float()
+            ev[:, :, 2] = torch.randint(0, W, (B, n), generator=gen).float()
+            ev[:, :, 3] = (torch.randint(0, 2, (B, n), generator=gen) * 2 - 1).float()
+        mk = torch.stack([(ev[:, :, 3] > 0).float(), (ev[:, :, 3] < 0).float()], -1)
+        return ev, mk
+
+    for t in range(P):
+        seq["flows"].append([syn.make_flow(gen, B, H, W, wl["sigma"]) for _ in range(F)])
+        ev, mk = window(N, t)
+        dev, dmk = window(Nd, t)
+        seq["events"].append(ev)
+        seq["masks"].append(mk)
+        seq["d_events"].append(dev)
+        seq["d_masks"].append(dmk)
+    return seq
+
+
+def events_per_step(wl, n_override=None):
+    N = wl["N"] if n_override is None else n_override
+    Nd = wl["Nd"] if n_override is None else (n_override if wl["Nd"] > 0 else 0)
+    return wl["B"] * wl["P"] * (N + Nd)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_port_step(seq, wl):
+    from oracle import cm_oracle as orc
+
+    cfg = orc.make_cfg(wl["B"], wl["H"], wl["W"], wl["P"], wl["F"], wl["S"], wl["mode"])
+    fn = orc.iterative if wl["warping"] == "Iterative" else orc.linear
+    t0 = time.perf_counter()
+    out = fn(cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], np.float32, want_grad=True)
+    return time.perf_counter() - t0, out
+
+
+def cpu_sample_size(wl):
+    # bounded sample: same resolution / passes / batch, fewer events per window
+    return min(wl["N"], 200_000)
+
+
+def run_cpu_baseline(wl, repeats=2):
+    n = cpu_sample_size(wl)
+    seq = fast_sequence(1234, wl, n_override=n)
+    cpu_port_step(seq, wl)  # warm-up (page faults, OpenMP pool)
+    best = min(cpu_port_step(seq, wl)[0] for _ in range(repeats))
+    ev = events_per_step(wl, n)
+    return {
+        "value": ev / best / 1e6, "unit": "Mevents/s", "cores": os.cpu_count(), "kind": "port",
+        "sample": "%s with %d events/window (%d events/step), oracle/cm_oracle.c fwd+bwd, OpenMP on %d threads, best of %d"
+                  % (wl["name"], n, ev, os.cpu_count(), repeats),
+    }
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = cpu_sample_size(wl)
+    seq = fast_sequence(1234, wl, n_override=n)
+    for _ in range(args.warmup):
+        cpu_port_step(seq, wl)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(seq, wl)
+    dt = time.perf_counter() - t0
+    ev = events_per_step(wl, n)
+    v = ev * args.steps / dt / 1e6
+    sample = "%s with %d events/window (%d events/step), CPU port of the reference algorithm (oracle/cm_oracle.c), OpenMP on %d threads" % (
+        wl["name"], n, ev, os.cpu_count())
+    line = {
+        "impl": "reference", "metric": "cm_loss_fwd_bwd_throughput", "value": v, "unit": "Mevents/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(wl),
+        "cpu_baseline": {"value": v, "unit": "Mevents/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(wl):
+    return {
+        "workload": wl["name"], "warping": wl["warping"], "iterative_mode": wl["mode"], "batch": wl["B"], "passes_loss": wl["P"],
+        "events_per_window": wl["N"], "detached_events_per_window": wl["Nd"], "resolution": [wl["H"], wl["W"]],
+        "flow_scales": wl["F"], "scales_loss": wl["S"], "event_distribution": wl["dist"], "flow_sigma_px": wl["sigma"],
+        "cache": "inputs_larger_than_L2 (fresh event tensors every step)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def kernel_bytes(wl, kernel):
+    """Algorithmic (compulsory) HBM bytes of one launch of the two event kernels."""
+    E = events_per_step(wl)
+    Eg = wl["B"] * wl["P"] * wl["N"]
+    maps = 8 * wl["F"] * wl["P"] * wl["B"] * wl["H"] * wl["W"]     # packed float2 flow maps
+    if kernel in ("iter_fwd_kernel", "linear_fwd_kernel"):
+        return 24 * E + maps
+    if kernel in ("iter_bwd_kernel", "linear_bwd_kernel"):
+        return 24 * Eg + 2 * maps
+    raise KeyError(kernel)
+
+
+def run_ours(args, wl):
+    import ctypes
+
+    import torch.distributed as dist
+
+    from taming_event_flow_b200 import _lib, synthetic as syn
+    from taming_event_flow_b200.loss import flow as tef_flow
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    L.tef_launch_count.restype = ctypes.c_long
+
+    seq = fast_sequence(100 + rank, wl)
+    P, F = wl["P"], wl["F"]
+    cfg = syn.loss_config(wl["H"], wl["W"], wl["B"], P, wl["S"], wl["mode"], warping=wl["warping"])
+    module = getattr(tef_flow, wl["warping"])(cfg, dev)
+    E = events_per_step(wl)
+    nsteps = args.warmup + args.steps
+
+    # ---- device-resident arm: fresh event tensors for every step (update() mutates ts in place)
+    d_flows = [[f.to(dev).requires_grad_(True) for f in per] for per in seq["flows"]]
+    d_masks = [m.to(dev) for m in seq["masks"]]
+    d_dmasks = [m.to(dev) for m in seq["d_masks"]]
+    ev_src = [e.to(dev) for e in seq["events"]]
+    dev_src = [e.to(dev) for e in seq["d_events"]]
+    ev_steps = [[e.clone() for e in ev_src] for _ in range(nsteps)]
+    dev_steps = [[e.clone() for e in dev_src] for _ in range(nsteps)]
+
+    def step_resident(i):
+        module.reset()
+        for t in range(P):
+            module.update(d_flows[t], ev_steps[i][t], d_masks[t], dev_steps[i][t], d_dmasks[t])
+        loss = module()
+        loss.backward()
+        for per in d_flows:
+            for f in per:
+                f.grad = None
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    L.tef_prof_reset()
+    L.tef_prof_enable(1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.tef_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.tef_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    L.tef_prof_enable(0)
+    loss_value = float(loss.item())
+
+    # per-kernel device time (CUDA events on the launching stream, recorded inside the library)
+    kern = {}
+    L.tef_prof_name.restype = ctypes.c_char_p
+    for k in range(L.tef_prof_num_kernels()):
+        tot, timed, cnt = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+        L.tef_prof_read(k, ctypes.byref(tot), ctypes.byref(timed), ctypes.byref(cnt))
+        if timed.value:
+            kern[L.tef_prof_name(k).decode()] = {"ms_total": tot.value, "launches": timed.value, "ms_avg": tot.value / timed.value}
+    del ev_steps, dev_steps
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: every input in pinned host memory, loss + gradients read back
+    h_flows = [[f.pin_memory() for f in per] for per in seq["flows"]]
+    h_masks = [m.pin_memory() for m in seq["masks"]]
+    h_dmasks = [m.pin_memory() for m in seq["d_masks"]]
+    h_ev = [e.pin_memory() for e in seq["events"]]
+    h_dev = [e.pin_memory() for e in seq["d_events"]]
+    h_grads = torch.empty((P, F, wl["B"], 2, wl["H"], wl["W"]), dtype=torch.float32).pin_memory()
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for per in h_flows for t in per) + sum(t.numel() * 4 for lst in (h_masks, h_dmasks, h_ev, h_dev) for t in lst)
+    d2h = h_grads.numel() * 4 + 4
+
+    def step_e2e():
+        module.reset()
+        flows = []
+        for t in range(P):
+            fl = [f.to(dev, non_blocking=True).requires_grad_(True) for f in h_flows[t]]
+            flows.append(fl)
+            module.update(fl, h_ev[t].to(dev, non_blocking=True), h_masks[t].to(dev, non_blocking=True),
+                          h_dev[t].to(dev, non_blocking=True), h_dmasks[t].to(dev, non_blocking=True))
+        loss = module()
+        loss.backward()
+        for t in range(P):
+            for f in range(F):
+                h_grads[t, f].copy_(flows[t][f].grad, non_blocking=True)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- aggregate over ranks (max time), whole-job throughput
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = times.tolist()
+    value = world * E * args.steps / (ms * 1e-3) / 1e6
+    e2e_value = world * E * e2e_steps / (ms_e2e * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak_src = "fallback (B200_PROFILING.md)"
+        hbm = 6650.0
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+            hbm = float(peaks.get("hbm_gbs", hbm))
+            peak_src = "measured (MEASURED_PEAKS.json)"
+        cand = [k for k in ("iter_fwd_kernel", "iter_bwd_kernel", "linear_fwd_kernel", "linear_bwd_kernel") if k in kern]
+        dom = max(cand, key=lambda k: kern[k]["ms_total"])
+        nbytes = kernel_bytes(wl, dom)
+        achieved = nbytes / (kern[dom]["ms_avg"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(wl["name"], {}).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": nbytes, "kernel_ms_avg": kern[dom]["ms_avg"], "peak_source": peak_src,
+                    "kernel_share_of_step": kern[dom]["ms_total"] / ms}
+        cpu = run_cpu_baseline(wl)
+        line = {
+            "metric": "cm_loss_fwd_bwd_throughput", "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"], "share_of_step": round(v["ms_total"] / ms, 4)} for k, v in kern.items()},
+            "loss": loss_value, "events_per_step_per_gpu": E,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+/*
+ * tef_b200.h -- C ABI of the B200 (sm_100a) contrast-maximization library.
+ *
+ * The reference (tudelft/taming_event_flow) is pure Python/PyTorch and has no FFI;
+ * the boundary it offers is the Python surface of utils/iwe.py, loss/flow.py and
+ * dataloader/encodings.py.  Each entry point below names the
+ * reference function it replaces; the Python host mirror in
+ * taming_event_flow_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name says host; buffers are
+ *     owned and allocated by the caller, nothing is allocated inside;
+ *   - all arithmetic is fp32; tensors are contiguous, row-major, laid out as the
+ *     reference's tensors unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
+ *   - return value: 0 on success, a positive cudaError_t from the launch, or a
+ *     negative TEF_E* argument error.  tef_strerror() explains both.
+ */
+#ifndef TEF_B200_H
+#define TEF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEF_MAX_PASSES 40   /* passes_loss (after the mode-"four" doubling)          */
+#define TEF_MAX_SCALES 6    /* scales_loss                                            */
+#define TEF_MAX_FLOWS 8     /* flow maps per pass (RecEVFlowNet emits 4)              */
+
+#define TEF_EINVAL (-1)     /* bad size / null pointer                                */
+#define TEF_ELIMIT (-2)     /* configuration beyond the static limits above           */
+#define TEF_EEMPTY (-3)     /* empty window list: reference raises RuntimeError (torch.cat of []) */
+#define TEF_EMODE4 (-4)     /* mode "four" + border compensation: reference raises TypeError       */
+
+int tef_version(void);
+const char *tef_strerror(int code);
+
+/* ------------------------------------------------------------------------- */
+/* Fused CM loss (loss/flow.py: Iterative :415-746, Linear :216-412)          */
+/* ------------------------------------------------------------------------- */
+typedef struct tef_cm_desc {
+    int B, H, W;           /* batch, resolution (config["loader"]["resolution"])      */
+    int P;                 /* passes in the loss window = max(passes_loss)            */
+    int F;                 /* number of flow maps per pass (len(flow_list))           */
+    int S;                 /* config["data"]["scales_loss"]                           */
+    int mode;              /* iterative_mode: 1 one, 2 two, 4 four (ignored by Linear) */
+    int border_comp;       /* BaseEventWarping.border_compensation                    */
+    int loss_scaling;      /* BaseEventWarping.loss_scaling                           */
+    int deterministic;     /* 0: fp32 RED accumulation; 1: order-independent fixed point (bit-reproducible) */
+    /* staged events, set 0 = with gradient, set 1 = detached; pass t holds [B][n] rows:
+       ev = float4 (ts + t, y, x, p), mk = float2 (pos, neg).  Written by tef_stage_events. */
+    const void *ev[2][TEF_MAX_PASSES];
+    const void *mk[2][TEF_MAX_PASSES];
+    int n[2][TEF_MAX_PASSES];
+    /* Linear only: per-event flow sampled at update time, float2 (y, x), [F][B*n] per pass */
+    void *evflow[2][TEF_MAX_PASSES];
+    const void *flow;      /* packed flow maps, float2 (x, y): [F][P][B][H][W]         */
+    void *gflow;           /* gradient of the packed maps, same layout (backward)      */
+    void *img;             /* float4 (cnt+, ts+, cnt-, ts-) per pixel: [F][B][slots][H][W]; after backward
+                              it holds the gradient images (dL/dcnt+, dL/dts+, dL/dcnt-, dL/dts-)         */
+    double *acc_sum;       /* [F][B][slots] sum of squared normalised timestamps       */
+    int *acc_nnz;          /* [F][B][slots] pixels with at least one event             */
+    float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
+    float *loss;           /* [1] scalar loss                                          */
+    const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
+} tef_cm_desc;
+
+/* number of image slots (scale, sub-window, tref) per (flow map, sample)             */
+int tef_cm_num_slots(const tef_cm_desc *d, int linear);
+
+/* Iterative.update / Linear.update, event part (loss/flow.py:456-473, :246-263):
+   ts += pass_index IN PLACE in the caller's [B,n,4] tensor, then (ts | ts_override), y, x, p
+   and the mask are copied into the staging buffers.  ts_override: device scalar for
+   round_ts (loss/flow.py:461-463) or NULL. */
+int tef_stage_events(void *events_inout, const void *pol_mask, void *ev_out, void *mk_out,
+                     long rows, float pass_index, const float *ts_override, void *stream);
+
+/* update_base (loss/flow.py:46-66): one pass of F flow maps [B,2,H,W] (ch0 = x, ch1 = y)
+   interleaved into the packed buffer at pass `t`. */
+int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B, int H, int W,
+                  void *packed, void *stream);
+/* backward counterpart: packed gradient -> [P][F][B][2][H][W] */
+int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, void *stream);
+
+/* Iterative.forward (loss/flow.py:588-746) and its analytic backward */
+int tef_iterative_forward(const tef_cm_desc *d, void *stream);
+int tef_iterative_backward(const tef_cm_desc *d, void *stream);
+
+/* Linear.update, flow part (loss/flow.py:266-285), Linear.forward (:306-412) and backward */
+int tef_linear_sample(const tef_cm_desc *d, int t, void *stream);
+int tef_linear_forward(const tef_cm_desc *d, void *stream);
+int tef_linear_backward(const tef_cm_desc *d, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* utils/iwe.py primitives                                                    */
+/* ------------------------------------------------------------------------- */
+/* event_propagation (utils/iwe.py:5-14): out = loc + (tref - ts) * flow; ts [n], others [n][2] */
+int tef_event_propagation(const float *ts, const float *loc, const float *flow, float tref, float *out, long n, void *stream);
+int tef_event_propagation_bwd(const float *gout, const float *ts, const float *flow, float tref,
+                              float *g_ts, float *g_loc, float *g_flow, long n, void *stream);
+/* get_event_flow (utils/iwe.py:17-40): maps [B][H][W], loc [B][N][2] (y,x) -> out [B][N][2] (y,x) */
+int tef_get_event_flow(const float *mapx, const float *mapy, const float *loc, float *out, int B, int N, int H, int W, void *stream);
+/* g_mapx/g_mapy must be zeroed by the caller; g_loc is written */
+int tef_get_event_flow_bwd(const float *gout, const float *mapx, const float *mapy, const float *loc,
+                           float *g_mapx, float *g_mapy, float *g_loc, int B, int N, int H, int W, void *stream);
+/* purge_unfeasible (utils/iwe.py:43-60); rows of [n][2]; also usable as its own backward (g * in) */
+int tef_purge_unfeasible(const float *loc, const float *mask, float *out_loc, float *out_mask, long n, int H, int W, void *stream);
+int tef_purge_unfeasible_bwd(const float *loc, const float *g_loc_out, const float *g_mask_out, float *g_loc, float *g_mask, long n, int H, int W, void *stream);
+/* get_interpolation (utils/iwe.py:63-113): warped [B][N][2] -> idx, w [B][4N] (corner-major) or [B][N] when round_idx */
+int tef_get_interpolation(const float *warped, float *idx, float *w, int B, int N, int H, int W, int round_idx, void *stream);
+int tef_get_interpolation_bwd(const float *warped, const float *g_w, float *g_warped, int B, int N, int H, int W, void *stream);
+/* interpolate (utils/iwe.py:116-136): iwe [B][H*W] must hold zeros or the `zeros` start image; pol may be NULL */
+int tef_interpolate(const float *idx, const float *w, const float *pol, float *iwe, int B, long M, int H, int W, void *stream);
+int tef_interpolate_bwd(const float *idx, const float *pol, const float *w, const float *g_iwe, float *g_w, float *g_pol, int B, long M, int H, int W, void *stream);
+/* deblur_events (utils/iwe.py:139-224): flow [B][2][H][W], events [B][N][4], pol [B][N] or NULL -> iwe [B][H*W] (zeroed inside) */
+int tef_deblur_events(const float *flow, const float *events, const float *pol, float *iwe, int B, int N, int H, int W,
+                      int round_idx, int round_flow, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* dataloader/encodings.py                                                    */
+/* ------------------------------------------------------------------------- */
+/* events_to_image (:8-29): img [H][W] zeroed inside; accumulate=0 keeps the reference's last-writer-wins put */
+int tef_events_to_image(const float *xs, const float *ys, const float *ps, float *img, long n, int H, int W, int accumulate, void *stream);
+/* events_to_channels (:59-81): out [2][H][W] */
+int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, void *stream);
+/* events_to_voxel (:32-56): out [bins][H][W] */
+int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* launch accounting / per-kernel timing (used by bench.py for gpu_launches   */
+/* and the roofline; CUDA events are recorded on the launching stream)        */
+/* ------------------------------------------------------------------------- */
+void tef_prof_enable(int on);
+void tef_prof_reset(void);
+int tef_prof_num_kernels(void);
+const char *tef_prof_name(int id);
+int tef_prof_read(int id, double *ms_total, long *timed_launches, long *launches);
+long tef_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEF_B200_H */

@@ -1,0 +1,96 @@
+// tef_cm_io.cu -- staging kernels of the loss modules' `update` / gradient hand-back:
+// event staging (loss/flow.py:456-473), flow-map packing (update_base, :46-66) and
+// unpacking of the packed flow gradient.  All three are pure HBM streaming kernels
+// (vectorised 16 B accesses, grid sized in multiples of the SM count by the caller).
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+__global__ void __launch_bounds__(kThreads) stage_events_kernel(float4 *__restrict__ ev_inout, const float2 *__restrict__ mk_in,
+                                                                float4 *__restrict__ ev_out, float2 *__restrict__ mk_out, long rows,
+                                                                float pass_index, const float *__restrict__ ts_override) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= rows) return;
+    float4 e = ev_inout[i];
+    e.x = e.x + pass_index;                 // event_list[:, :, 0:1] += self._passes (in place, :457)
+    ev_inout[i] = e;
+    if (ts_override) e.x = __ldg(ts_override);   // round_ts (:461-463)
+    ev_out[i] = e;
+    mk_out[i] = mk_in[i];
+}
+
+struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
+
+// [B][2][H][W] planar (ch0 = x, ch1 = y) -> float2 interleaved [B][H][W]
+__global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_constant__ FlowPtrs src, float2 *__restrict__ packed, int t, int P,
+                                                             int B, long HW) {
+    const int f = blockIdx.z, b = blockIdx.y;
+    const float *sx = src.p[f] + (long)b * 2 * HW, *sy = sx + HW;
+    float2 *dst = packed + (((long)f * P + t) * B + b) * HW;
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < HW; i += (long)gridDim.x * kThreads)
+        dst[i] = make_float2(sx[i], sy[i]);
+}
+
+// packed gradient [F][P][B][H][W] float2 -> [P][F][B][2][H][W]
+__global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__restrict__ packed, float *__restrict__ out, int F, int P, int B,
+                                                               long HW) {
+    const int fp = blockIdx.z, b = blockIdx.y;
+    const int f = fp / P, t = fp % P;
+    const float2 *src = packed + (((long)f * P + t) * B + b) * HW;
+    float *ox = out + ((((long)t * F + f) * B + b) * 2) * HW, *oy = ox + HW;
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < HW; i += (long)gridDim.x * kThreads) {
+        const float2 g = src[i];
+        ox[i] = g.x; oy[i] = g.y;
+    }
+}
+
+}  // namespace tef
+
+using namespace tef;
+
+extern "C" int tef_stage_events(void *events_inout, const void *pol_mask, void *ev_out, void *mk_out, long rows, float pass_index,
+                                const float *ts_override, void *stream) {
+    if (rows < 0) return TEF_EINVAL;
+    if (rows == 0) return 0;
+    if (!events_inout || !pol_mask || !ev_out || !mk_out) return TEF_EINVAL;
+    ProfScope ps(K_STAGE_EVENTS, (cudaStream_t)stream);
+    stage_events_kernel<<<(unsigned)((rows + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        (float4 *)events_inout, (const float2 *)pol_mask, (float4 *)ev_out, (float2 *)mk_out, rows, pass_index, ts_override);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B, int H, int W, void *packed, void *stream) {
+    if (!flow_maps_host || !packed || F < 1 || F > TEF_MAX_FLOWS || t < 0 || t >= P || B < 1) return TEF_EINVAL;
+    FlowPtrs src;
+    for (int f = 0; f < F; ++f) { if (!flow_maps_host[f]) return TEF_EINVAL; src.p[f] = (const float *)flow_maps_host[f]; }
+    const long HW = (long)H * W;
+    int bx = (int)((HW + kThreads - 1) / kThreads);
+    if (bx > 148 * 4) bx = 148 * 4;
+    ProfScope ps(K_PACK_FLOW, (cudaStream_t)stream);
+    pack_flow_kernel<<<dim3(bx, B, F), kThreads, 0, (cudaStream_t)stream>>>(src, (float2 *)packed, t, P, B, HW);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, void *stream) {
+    if (!packed || !out || F < 1 || P < 1 || B < 1) return TEF_EINVAL;
+    const long HW = (long)H * W;
+    int bx = (int)((HW + kThreads - 1) / kThreads);
+    if (bx > 148 * 4) bx = 148 * 4;
+    ProfScope ps(K_UNPACK_GRAD, (cudaStream_t)stream);
+    unpack_grad_kernel<<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, HW);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_version(void) { return 100; }
+
+extern "C" const char *tef_strerror(int code) {
+    switch (code) {
+        case 0: return "success";
+        case TEF_EINVAL: return "invalid argument (size or null pointer)";
+        case TEF_ELIMIT: return "configuration beyond the library's static limits (TEF_MAX_*)";
+        case TEF_EEMPTY: return "empty window list (the reference raises RuntimeError: torch.cat of an empty list)";
+        case TEF_EMODE4: return "iterative_mode 'four' with border compensation (the reference raises TypeError)";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}

@@ -1,0 +1,278 @@
+// tef_cm_iterative.cu -- fused Iterative contrast-maximization loss for sm_100a.
+//
+// Replaces Iterative.forward + autograd (upstream loss/flow.py:492-746, utils/iwe.py)
+// with three phases separated by the two global dependencies of the loss
+// (SURVEY.md §7 hard part 3):
+//
+//   iter_fwd_kernel   one thread per (event, flow scale): walks the whole warping
+//                     chain on chip (positions at every reference time), forms
+//                     the shared border mask, and splats count + time-weighted
+//                     images straight into L2-resident slot images with native
+//                     vector reductions (REDG.E.ADD.F32x2).  No per-event
+//                     intermediate (positions, indices, weights) ever reaches HBM.
+//   iwe_reduce/finalize   per-pixel normalisation, sum of squares, non-zero count.
+//   iwe_grad_kernel + iter_bwd_kernel   gradient images in place, then one thread
+//                     per gradient-carrying event: recompute the chain, gather the
+//                     gradient images at the corners, walk the chain in reverse and
+//                     reduce into the packed flow-gradient maps (REDG F32x2).
+//
+// Shared-memory tiles are deliberately NOT used: on sm_100a fp32 atomicAdd on
+// shared memory compiles to an ATOMS.CAST.SPIN compare-and-swap loop, whereas
+// global fp32 reductions are native fire-and-forget REDG ops served by the L2
+// (126 MB, holds all slot images of every benchmark configuration).  See DESIGN.md.
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+// ---------------------------------------------------------------------------------
+// per-event chain (loss/flow.py:521-586): node positions for tref = 0..P.  The positions
+// live in shared memory as pos[tref][thread] (conflict-free, 8 B per lane), which keeps the
+// loops rolled and the register count low for any P; they never travel to HBM.
+// The pass index t is uniform per CTA, so the loop bounds do not diverge.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_f, int b, int t,
+                                               float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */) {
+    const long HW = (long)p.H * p.W;
+    uint64_t alive = 0;
+    float y = y0, x = x0, tprev = ts;
+    bool al = true;
+    for (int tr = t + 1; tr <= p.P; ++tr) {        // forward: sample map tr-1, land on node tr
+        if (al) {
+            const float2 *map = flow_f + ((long)(tr - 1) * p.B + b) * HW;
+            float2 v = sample_flow<false>(map, p.res, y, x, nullptr);
+            float dt = (float)tr - tprev;          // utils/iwe.py:14
+            y = y + dt * v.y; x = x + dt * v.x;
+            al = inside(y, x, p.res);              // utils/iwe.py:52-59
+            if (al) alive |= (1ull << tr);
+        }
+        tprev = (float)tr;
+        pos[tr * kThreads + threadIdx.x] = make_float2(y, x);
+    }
+    y = y0; x = x0; tprev = ts; al = true;
+    for (int tr = t; tr >= 0; --tr) {              // backward: sample map tr, land on node tr
+        if (al) {
+            const float2 *map = flow_f + ((long)tr * p.B + b) * HW;
+            float2 v = sample_flow<false>(map, p.res, y, x, nullptr);
+            float dt = (float)tr - tprev;
+            y = y + dt * v.y; x = x + dt * v.x;
+            al = inside(y, x, p.res);
+            if (al) alive |= (1ull << tr);
+        }
+        tprev = (float)tr;
+        pos[tr * kThreads + threadIdx.x] = make_float2(y, x);
+    }
+    return alive;
+}
+
+// sub-window bookkeeping of one temporal scale for an event of pass t (loss/flow.py:657-686)
+struct Win {
+    int lo, hi, low_tref, high_tref, delta, slot0;
+    bool shared_ok;
+};
+__device__ __forceinline__ bool window_of(const CmParams &p, int s, int t, uint64_t alive, Win &w) {
+    const int L = p.sc.L[s];
+    if (t >= (L << s)) return false;               // passes beyond 2^s windows are unused at this scale
+    const int wi = t / L;
+    w.delta = p.sc.delta[s];
+    w.lo = wi * L; w.hi = w.lo + L;
+    w.low_tref = w.lo; w.high_tref = w.hi + 1;
+    if (p.mode == 4) { w.low_tref = w.lo + w.delta; w.high_tref = w.lo + 3 * w.delta + 1; }
+    const uint64_t m = ((1ull << w.high_tref) - 1ull) & ~((1ull << w.low_tref) - 1ull);
+    w.shared_ok = (alive & m) == m;                // product of the masks over all tref (:671-681)
+    w.slot0 = p.sc.slot_base[s] + wi * p.sc.ntau[s] - w.low_tref;
+    return true;
+}
+__device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
+    if (tr < w.low_tref || tr >= w.high_tref) return false;
+    const int lo_e = max(w.lo, tr - w.delta), hi_e = min(w.hi, tr + w.delta);   // :685-686
+    return t >= lo_e && t < hi_e;
+}
+
+__global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constant__ CmParams p) {
+    extern __shared__ float2 pos[];
+    int sg = 0;
+    const int blk = blockIdx.x;
+    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
+    const int n = p.seg.n[sg], t = p.seg.pass[sg];
+    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    if (row >= (long)p.B * n) return;
+    const float2 m = __ldg(p.seg.mk[sg] + row);
+    if (m.x == 0.0f && m.y == 0.0f) return;        // padding rows contribute nothing
+    const float4 e = __ldg(p.seg.ev[sg] + row);
+    const int b = (int)(row / n), f = blockIdx.y;
+    const long HW = (long)p.H * p.W;
+    const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
+
+    const uint64_t alive = warp_chain(p, flow_f, b, t, e.x, e.y, e.z, pos);
+
+    float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+    for (int s = 0; s < p.sc.S; ++s) {
+        Win w;
+        if (!window_of(p, s, t, alive, w)) continue;
+        if (p.border && !w.shared_ok) continue;
+        const float fdelta = (float)w.delta;
+        // reference times fed by window t: max(lo, tr-delta) <= t < min(hi, tr+delta)  (:685-686)
+        const int tr0 = max(w.low_tref, t - w.delta + 1), tr1 = min(w.high_tref - 1, t + w.delta);
+        for (int tr = tr0; tr <= tr1; ++tr) {
+            if (!p.border && !((alive >> tr) & 1ull)) continue;
+            const float nts = 1.0f - fabsf((float)tr - e.x) / fdelta;         // loss/flow.py:94-95
+            const float2 q = pos[tr * kThreads + threadIdx.x];
+            splat(img_fb + (long)(w.slot0 + tr) * HW, p.res, q.x, q.y, nts, m);
+        }
+    }
+}
+
+// one reverse chain step: reduce dL/dmap, return dL/d(source position)
+__device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, float sy, float sx,
+                                         float dt, float gpy, float gpx, float &cy_, float &cx_) {
+    Taps tp;
+    sample_flow<true>(map, r, sy, sx, &tp);
+    float2 *g = gmap + (long)tp.y0 * r.W + tp.x0;
+    const int off[4] = { 0, 1, r.W, r.W + 1 };
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (tp.ok[k]) { const float c = dt * tp.w[k]; red_add_v2(g + off[k], c * gpx, c * gpy); }
+    const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
+    const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
+    const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
+    const float dvx_dx = (1.0f - tp.ay) * (tp.v[1].x - tp.v[0].x) + tp.ay * (tp.v[3].x - tp.v[2].x);
+    cy_ = gpy + dt * (dvy_dy * gpy + dvx_dy * gpx);
+    cx_ = gpx + dt * (dvy_dx * gpy + dvx_dx * gpx);
+}
+
+__global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constant__ CmParams p) {
+    extern __shared__ float2 pos[];
+    int sg = 0;
+    const int blk = blockIdx.x;
+    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
+    const int n = p.seg.n[sg], t = p.seg.pass[sg];
+    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    if (row >= (long)p.B * n) return;
+    const float2 m = __ldg(p.seg.mk[sg] + row);
+    if (m.x == 0.0f && m.y == 0.0f) return;
+    const float4 e = __ldg(p.seg.ev[sg] + row);
+    const int b = (int)(row / n), f = blockIdx.y;
+    const long HW = (long)p.H * p.W;
+    const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
+    float2 *gflow_f = p.gflow + (long)f * p.P * p.B * HW;
+    const float ts = e.x, y0 = e.y, x0 = e.z;
+
+    const uint64_t alive = warp_chain(p, flow_f, b, t, ts, y0, x0, pos);
+
+    // windows of every scale, and the range of nodes that receive an image gradient
+    Win win[TEF_MAX_SCALES];
+    int lo_node = p.P + 1, hi_node = -1;
+    uint32_t has = 0;
+    for (int s = 0; s < p.sc.S; ++s) {
+        if (!window_of(p, s, t, alive, win[s])) continue;
+        if (p.border && !win[s].shared_ok) continue;
+        has |= 1u << s;
+        lo_node = min(lo_node, max(win[s].low_tref, t - win[s].delta + 1));
+        hi_node = max(hi_node, min(win[s].high_tref - 1, t + win[s].delta));
+    }
+    if (!has) return;
+    const float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+
+    auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
+        for (int s = 0; s < p.sc.S; ++s) {
+            if (!((has >> s) & 1u) || !feeds(win[s], tr, t)) continue;
+            const float nts = 1.0f - fabsf((float)tr - ts) / (float)win[s].delta;
+            iwe_grad(img_fb + (long)(win[s].slot0 + tr) * HW, p.res, q.x, q.y, nts, m, gy, gx);
+        }
+    };
+
+    // reverse of the forward chain: nodes hi_node .. t+1 (nodes beyond carry no gradient)
+    float cy_ = 0.f, cx_ = 0.f;
+    for (int tr = min(hi_node, p.P); tr >= t + 1; --tr) {
+        const bool al = ((alive >> tr) & 1ull) != 0;
+        float gy = 0.f, gx = 0.f;
+        if (al) node_grad(tr, pos[tr * kThreads + threadIdx.x], gy, gx);
+        const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+        cy_ = 0.f; cx_ = 0.f;
+        if (gpy != 0.f || gpx != 0.f) {
+            const bool first = (tr - 1 == t);
+            const float2 src = first ? make_float2(y0, x0) : pos[(tr - 1) * kThreads + threadIdx.x];
+            const float dt = first ? ((float)tr - ts) : 1.0f;
+            const long mo = ((long)(tr - 1) * p.B + b) * HW;
+            step_bwd(flow_f + mo, gflow_f + mo, p.res, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+        }
+    }
+    // reverse of the backward chain: nodes lo_node .. t
+    cy_ = 0.f; cx_ = 0.f;
+    for (int tr = max(lo_node, 0); tr <= t; ++tr) {
+        const bool al = ((alive >> tr) & 1ull) != 0;
+        float gy = 0.f, gx = 0.f;
+        if (al) node_grad(tr, pos[tr * kThreads + threadIdx.x], gy, gx);
+        const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+        cy_ = 0.f; cx_ = 0.f;
+        if (gpy != 0.f || gpx != 0.f) {
+            const bool first = (tr == t);
+            const float2 src = first ? make_float2(y0, x0) : pos[(tr + 1) * kThreads + threadIdx.x];
+            const float dt = first ? ((float)tr - ts) : -1.0f;
+            const long mo = ((long)tr * p.B + b) * HW;
+            step_bwd(flow_f + mo, gflow_f + mo, p.res, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+        }
+    }
+}
+
+}  // namespace tef
+
+// ---------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------
+using namespace tef;
+
+int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st);   // tef_cm_reduce.cu
+int tef_grad_images(const CmParams &p, cudaStream_t st);           // tef_cm_reduce.cu
+
+static size_t chain_smem(const CmParams &p) { return sizeof(float2) * (size_t)(p.P + 1) * kThreads; }
+
+static int launch_fwd(const CmParams &p, cudaStream_t st) {
+    if (p.seg.blk_off[p.seg.nseg] > 0) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(iter_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads)); attr = true; }
+        dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
+        ProfScope ps(K_ITER_FWD, st);
+        iter_fwd_kernel<<<grid, kThreads, chain_smem(p), st>>>(p);
+    }
+    return (int)cudaGetLastError();
+}
+static int launch_bwd(const CmParams &p, cudaStream_t st) {
+    if (p.seg.blk_off[p.seg.nseg] > 0) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(iter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads)); attr = true; }
+        dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
+        ProfScope ps(K_ITER_BWD, st);
+        iter_bwd_kernel<<<grid, kThreads, chain_smem(p), st>>>(p);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CmParams p;
+    int rc = fill_params(d, 0, false, p);
+    if (rc) return rc;
+    if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
+    const long HW = (long)p.H * p.W;
+    const long nimg = (long)p.F * p.B * p.nslots;
+    cudaMemsetAsync(p.img, 0, sizeof(float4) * nimg * HW, st);
+    rc = launch_fwd(p, st);
+    if (rc) return rc;
+    return tef_reduce_and_finalize(p, st);
+}
+
+extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CmParams p;
+    int rc = fill_params(d, 0, true, p);
+    if (rc) return rc;
+    if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out) return TEF_EINVAL;
+    const long HW = (long)p.H * p.W;
+    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * HW, st);
+    rc = tef_grad_images(p, st);
+    if (rc) return rc;
+    rc = launch_bwd(p, st);
+    return rc;
+}

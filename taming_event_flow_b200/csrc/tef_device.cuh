@@ -1,0 +1,108 @@
+// tef_device.cuh -- per-event device arithmetic shared by all kernels.
+//
+// The library is compiled with -fmad=false: every fp32 operation below rounds
+// exactly once, in the order written, which is the order of the reference's
+// eager PyTorch CPU path (one ATen kernel per operation).  The only fused
+// multiply-adds are the explicit __fmaf_rn calls in sample_flow(): ATen's
+// grid_sampler_2d accumulates its four taps as  nw*w0, fma(ne,w1,.), fma(sw,w2,.),
+// fma(se,w3,.)  (established bit-exactly against torch 2.11, see
+// tests/test_oracle_golden.py).  Division is IEEE (nvcc default -prec-div=true).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tef {
+
+struct Res {
+    int H, W;
+    float hm1, wm1;   // (float)(H-1), (float)(W-1)
+    float sh, sw;     // (H-1)/2, (W-1)/2  (ATen's align_corners=True scaling factor)
+    __host__ __device__ static Res make(int H, int W) {
+        Res r; r.H = H; r.W = W; r.hm1 = (float)(H - 1); r.wm1 = (float)(W - 1);
+        r.sh = r.hm1 / 2.0f; r.sw = r.wm1 / 2.0f; return r;
+    }
+};
+
+// purge_unfeasible (utils/iwe.py:52-57): inclusive bounds [0, res-1]
+__device__ __forceinline__ bool inside(float y, float x, const Res &r) {
+    return (y >= 0.0f) && (y <= (float)r.H - 1.0f) && (x >= 0.0f) && (x <= (float)r.W - 1.0f);
+}
+
+// bilinear flow sample = utils/iwe.py:17-40 + ATen grid_sampler_2d (zeros padding, align_corners=True)
+struct Taps {
+    float w[4];       // nw, ne, sw, se
+    float2 v[4];      // tap values (.x = x-flow, .y = y-flow), 0 outside the map
+    float ax, ay;     // fractional offsets along x / y
+    int y0, x0;
+    bool ok[4];
+};
+
+template <bool KEEP>
+__device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
+    float gy = (2.0f * y) / r.hm1 - 1.0f;          // utils/iwe.py:30
+    float gx = (2.0f * x) / r.wm1 - 1.0f;          // utils/iwe.py:31
+    float iy = (gy + 1.0f) * r.sh;                 // ATen unnormalize, align_corners=True
+    float ix = (gx + 1.0f) * r.sw;
+    float fy0 = floorf(iy), fx0 = floorf(ix);
+    float w_ = ix - fx0, e_ = 1.0f - w_;
+    float n_ = iy - fy0, s_ = 1.0f - n_;
+    float wt[4] = { s_ * e_, s_ * w_, n_ * e_, n_ * w_ };
+    int y0, x0;
+    if (!(fx0 >= -2.0f && fx0 <= (float)(r.W + 1) && fy0 >= -2.0f && fy0 <= (float)(r.H + 1))) { y0 = -2; x0 = -2; }
+    else { y0 = (int)fy0; x0 = (int)fx0; }
+    const bool oy0 = (y0 >= 0) & (y0 < r.H), oy1 = (y0 + 1 >= 0) & (y0 + 1 < r.H);
+    const bool ox0 = (x0 >= 0) & (x0 < r.W), ox1 = (x0 + 1 >= 0) & (x0 + 1 < r.W);
+    const bool ok[4] = { oy0 && ox0, oy0 && ox1, oy1 && ox0, oy1 && ox1 };
+    const float2 *p = map + (long)y0 * r.W + x0;
+    float2 v[4];
+    const float2 z = make_float2(0.f, 0.f);
+    v[0] = ok[0] ? __ldg(p) : z;
+    v[1] = ok[1] ? __ldg(p + 1) : z;
+    v[2] = ok[2] ? __ldg(p + r.W) : z;
+    v[3] = ok[3] ? __ldg(p + r.W + 1) : z;
+    float ox = v[0].x * wt[0], oy = v[0].y * wt[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { ox = __fmaf_rn(v[k].x, wt[k], ox); oy = __fmaf_rn(v[k].y, wt[k], oy); }
+    if (KEEP) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tp->w[k] = wt[k]; tp->v[k] = v[k]; tp->ok[k] = ok[k]; }
+        tp->ax = w_; tp->ay = n_; tp->y0 = y0; tp->x0 = x0;
+    }
+    return make_float2(ox, oy);   // (.x = x-flow, .y = y-flow)
+}
+
+// get_interpolation, bilinear branch (utils/iwe.py:85-107), one event
+struct Corners {
+    float cy[2], cx[2];   // top/bottom, left/right corner coordinates (as fp32)
+    float wy[2], wx[2];   // clamped 1-D weights
+    bool oky[2], okx[2];  // strict in-image tests (utils/iwe.py:103)
+};
+__device__ __forceinline__ void corners(float y, float x, const Res &r, Corners &c) {
+    c.cy[0] = floorf(y); c.cy[1] = floorf(y + 1.0f);
+    c.cx[0] = floorf(x); c.cx[1] = floorf(x + 1.0f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        c.wy[k] = fmaxf(0.0f, 1.0f - fabsf(y - c.cy[k]));
+        c.wx[k] = fmaxf(0.0f, 1.0f - fabsf(x - c.cx[k]));
+        c.oky[k] = (c.cy[k] >= 0.0f) && (c.cy[k] < (float)r.H);
+        c.okx[k] = (c.cx[k] >= 0.0f) && (c.cx[k] < (float)r.W);
+    }
+}
+
+// d/dv max(0, 1-|v-c|) with autograd's conventions: abs'(0)=0, max() ties split 1/2
+__device__ __forceinline__ float d1(float v, float c) {
+    float d = v - c;
+    float u = 1.0f - fabsf(d);
+    float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+    return (u > 0.0f) ? -sg : ((u == 0.0f) ? -0.5f * sg : 0.0f);
+}
+
+// native vector reduction: REDG.E.ADD.F32x2 on sm_100a (no return value requested)
+__device__ __forceinline__ void red_add_v2(float2 *addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+}  // namespace tef

@@ -1,0 +1,308 @@
+"""Contrast-maximization losses, drop-in for the reference's ``loss/flow.py``.
+
+Same classes, constructor arguments, ``update`` / ``reset`` / ``num_passes`` /
+``__call__`` protocol and config keys as upstream (``loss/flow.py:14-746``), but the
+whole loss -- event warping, IWE splatting, focus loss and the backward pass -- runs
+in the fused CUDA kernels of ``csrc/tef_cm_*.cu`` instead of ~16 k eager tensor ops.
+
+What `update` keeps per pass is the packed flow map (float2 interleaved) and a staged
+copy of the event rows; nothing of size O(passes^2 * events) is ever materialised.
+The returned loss is a 0-dim tensor wired into autograd: ``loss.backward()`` delivers
+gradients to every tensor of every ``flow_list`` handed to `update`.
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from .._lib import CmDesc, check, lib, ptr, require_cuda, stream
+
+_MODES = {"one": 1, "two": 2, "four": 4}
+
+
+class _Window:
+    """Device state of one loss window (between two `reset` calls)."""
+
+    def __init__(self):
+        self.flows = []        # flows[t][f]: the caller's tensors (autograd leaves of the loss)
+        self.packed = None     # [F,P,B,H,W,2]
+        self.ev = ([], [])     # staged events per pass, (grad set, detached set)
+        self.mk = ([], [])
+        self.n = ([], [])
+        self.evflow = ([], []) # Linear only
+        self.shape = None      # (F, B, H, W)
+        self.img = None
+        self.den = None
+        self.consumed = False
+
+
+class _CMLoss(torch.autograd.Function):
+    """loss = CM(flow maps); backward = analytic gradient w.r.t. every flow map."""
+
+    @staticmethod
+    def forward(ctx, module, window, *flat_flows):
+        loss = module._forward_kernels(window)
+        ctx.module, ctx.window = module, window
+        ctx.nflows = len(flat_flows)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        grads = ctx.module._backward_kernels(ctx.window, gout)     # [P,F,B,2,H,W]
+        P, F = grads.shape[0], grads.shape[1]
+        out = []
+        for t in range(len(ctx.window.flows)):
+            for f in range(F):
+                out.append(grads[t, f] if t < P else None)
+        return (None, None) + tuple(out)
+
+
+class BaseEventWarping(torch.nn.Module):
+    """Base class of the CM losses (upstream ``loss/flow.py:14-213``)."""
+
+    _linear = False
+
+    def __init__(self, config, device, loss_scaling=True, border_compensation=True):
+        super().__init__()
+        self.device = device
+        self.config = config
+        self.loss_scaling = loss_scaling
+        self.border_compensation = border_compensation
+        self.res = config["loader"]["resolution"]
+        self.batch_size = config["loader"]["batch_size"]
+        self.flow_spat_smooth_weight = config["loss"]["flow_spat_smooth_weight"]
+        self.flow_temp_smooth_weight = config["loss"]["flow_temp_smooth_weight"]
+        self.deterministic = bool(config["loss"].get("deterministic", False))
+
+        self._passes = 0
+        self._num_flows = None
+        self._win = _Window()
+
+        # timescales for loss computation (loss/flow.py:42-44)
+        self.passes_loss = [config["data"]["passes_loss"] // (2 ** s) for s in range(config["data"]["scales_loss"])]
+
+    # ------------------------------------------------------------------ state
+    @property
+    def num_passes(self):
+        return self._passes
+
+    def reset_base(self):
+        self._passes = 0
+        self._win = _Window()      # a pending autograd graph keeps its own reference to the old window
+
+    def reset(self):
+        self.reset_base()
+
+    def _max_passes(self):
+        return max(self.passes_loss)
+
+    # ----------------------------------------------------------------- update
+    def update_base(self, flow_list):
+        """Pack this pass' flow maps (upstream ``update_base``, loss/flow.py:46-66)."""
+        w = self._win
+        if self._num_flows is None:
+            self._num_flows = len(flow_list)
+        if len(flow_list) != self._num_flows:
+            raise ValueError("flow_list has %d maps, expected %d" % (len(flow_list), self._num_flows))
+        require_cuda(*flow_list)
+        F = self._num_flows
+        B, C, H, W = flow_list[0].shape
+        if C != 2 or [H, W] != list(self.res):
+            raise ValueError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(flow_list[0].shape)))
+        if F > _lib.MAX_FLOWS:
+            raise _lib.TefError("at most %d flow maps per pass" % _lib.MAX_FLOWS)
+        P = self._max_passes()
+        if w.packed is None:
+            w.shape = (F, B, H, W)
+            w.packed = torch.empty((F, P, B, H, W, 2), dtype=torch.float32, device=flow_list[0].device)
+        w.flows.append(list(flow_list))
+        t = self._passes
+        if t < P:
+            srcs = [fl.detach().contiguous().float() for fl in flow_list]
+            arr = (ctypes.c_void_p * F)(*[s.data_ptr() for s in srcs])
+            check(lib().tef_pack_flow(arr, F, t, P, B, H, W, ptr(w.packed), stream()), "tef_pack_flow")
+
+    def _stage(self, k, events, mask):
+        """Event part of `update` (loss/flow.py:456-473): ts += passes in place, keep a staged copy."""
+        w = self._win
+        require_cuda(events, mask)
+        B, N = events.shape[0], events.shape[1]
+        rows = B * N
+        override = None
+        direct = events.is_contiguous() and events.dtype == torch.float32
+        if self.config["loss"]["round_ts"]:
+            # event_ts[...] = event_ts.min() + 0.5 (:461-463); min() of an empty tensor raises, like upstream
+            override = (events[:, :, 0].min() + float(self._passes) + 0.5).float().reshape(1)
+        ev_out = torch.empty((B, N, 4), dtype=torch.float32, device=events.device)
+        mk_out = torch.empty((B, N, 2), dtype=torch.float32, device=events.device)
+        if rows > 0:
+            if direct:
+                src, pass_index = events, float(self._passes)
+            else:
+                events[:, :, 0:1] += self._passes
+                src, pass_index = events.contiguous().float(), 0.0
+            mk = mask.contiguous().float()
+            check(lib().tef_stage_events(ptr(src), ptr(mk), ptr(ev_out), ptr(mk_out), ctypes.c_long(rows),
+                                         ctypes.c_float(pass_index), ptr(override), stream()), "tef_stage_events")
+        w.ev[k].append(ev_out)
+        w.mk[k].append(mk_out)
+        w.n[k].append(N)
+
+    def _update_events(self, event_list, pol_mask, d_event_list, d_pol_mask):
+        self._stage(0, event_list, pol_mask)
+        self._stage(1, d_event_list, d_pol_mask)
+
+    # ---------------------------------------------------------------- kernels
+    def _desc(self, w):
+        F, B, H, W = w.shape
+        P = self._max_passes()
+        d = CmDesc()
+        d.B, d.H, d.W, d.P, d.F = B, H, W, P, F
+        d.S = self.config["data"]["scales_loss"]
+        d.mode = 0 if self._linear else _MODES[self.config["loss"]["iterative_mode"]]
+        d.border_comp = int(bool(self.border_compensation))
+        d.loss_scaling = int(bool(self.loss_scaling))
+        d.deterministic = int(self.deterministic)
+        for k in range(2):
+            for t in range(P):
+                d.ev[k][t] = w.ev[k][t].data_ptr()
+                d.mk[k][t] = w.mk[k][t].data_ptr()
+                d.n[k][t] = w.n[k][t]
+                if self._linear:
+                    d.evflow[k][t] = w.evflow[k][t].data_ptr()
+        d.flow = w.packed.data_ptr()
+        return d
+
+    def _forward_kernels(self, w):
+        F, B, H, W = w.shape
+        d = self._desc(w)
+        nslots = lib().tef_cm_num_slots(ctypes.byref(d), int(self._linear))
+        check(min(nslots, 0), "tef_cm_num_slots")
+        dev = w.packed.device
+        w.img = torch.empty((F, B, nslots, H, W, 4), dtype=torch.float32, device=dev)
+        w.acc_sum = torch.empty((F, B, nslots), dtype=torch.float64, device=dev)
+        w.acc_nnz = torch.empty((F, B, nslots), dtype=torch.int32, device=dev)
+        w.den = torch.empty((F, B, nslots), dtype=torch.float32, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        d.img, d.acc_sum, d.acc_nnz, d.den, d.loss = (x.data_ptr() for x in (w.img, w.acc_sum, w.acc_nnz, w.den, loss))
+        fn = lib().tef_linear_forward if self._linear else lib().tef_iterative_forward
+        check(fn(ctypes.byref(d), stream()), "tef_linear_forward" if self._linear else "tef_iterative_forward")
+        w.consumed = False
+        return loss.view(())
+
+    def _backward_kernels(self, w, gout):
+        if w.consumed:
+            raise RuntimeError("the CM loss graph has already been back-propagated (the image buffers are reused in place)")
+        F, B, H, W = w.shape
+        P = self._max_passes()
+        d = self._desc(w)
+        dev = w.packed.device
+        gpacked = torch.empty((F, P, B, H, W, 2), dtype=torch.float32, device=dev)
+        grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)
+        g = gout.detach().float().contiguous().reshape(1)
+        d.img, d.den, d.gflow, d.grad_out = w.img.data_ptr(), w.den.data_ptr(), gpacked.data_ptr(), g.data_ptr()
+        fn = lib().tef_linear_backward if self._linear else lib().tef_iterative_backward
+        check(fn(ctypes.byref(d), stream()), "tef_linear_backward" if self._linear else "tef_iterative_backward")
+        check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, stream()), "tef_unpack_flow_grad")
+        w.consumed = True
+        return grads
+
+    # ---------------------------------------------------------------- forward
+    def _cm_loss(self):
+        w = self._win
+        P = self._max_passes()
+        if self._passes < P or w.packed is None:
+            # upstream indexes lists of length num_passes with range(max_passes)
+            raise IndexError("the loss window needs %d passes, only %d were given to update()" % (P, self._passes))
+        flat = [fl for per_pass in w.flows for fl in per_pass]
+        if torch.is_grad_enabled() and any(fl.requires_grad for fl in flat):
+            return _CMLoss.apply(self, w, *flat)
+        return self._forward_kernels(w)
+
+    def _smoothing_terms(self, loss):
+        if self.flow_spat_smooth_weight is not None:
+            loss = loss + self.flow_spatial_smoothing()
+        if self.flow_temp_smooth_weight is not None and self._passes > 1:
+            loss = loss + self.flow_temporal_smoothing()
+        return loss
+
+    def flow_spatial_smoothing(self):
+        raise NotImplementedError("flow_spat_smooth_weight is not None: the smoothness priors (upstream loss/flow.py:131-209) "
+                                  "are outside the accelerated path (SURVEY.md §8f-3)")
+
+    def flow_temporal_smoothing(self):
+        raise NotImplementedError("flow_temp_smooth_weight is not None: the smoothness priors (upstream loss/flow.py:131-209) "
+                                  "are outside the accelerated path (SURVEY.md §8f-3)")
+
+    def forward(self):
+        raise NotImplementedError
+
+
+class Iterative(BaseEventWarping):
+    """CM loss with iterative warping, all intermediate reference times and several temporal
+    scales (upstream ``loss/flow.py:415-746``)."""
+
+    def __init__(self, config, device, loss_scaling=True):
+        if config["loss"]["iterative_mode"] == "four":
+            config["data"]["passes_loss"] *= 2          # upstream mutates the caller's config (:422-423)
+        super().__init__(config, device, loss_scaling=loss_scaling)
+        mode = config["loss"]["iterative_mode"]
+        self.delta_passes = []
+        for passes in self.passes_loss:
+            if mode in _MODES:
+                self.delta_passes.append(passes // _MODES[mode])
+
+    def update(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
+        """Same contract as upstream ``Iterative.update`` (:443-476), including the in-place
+        ``event_list[:, :, 0] += num_passes`` on the caller's tensors."""
+        self.update_base(flow_list)
+        self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
+        self._passes += 1
+
+    def forward(self):
+        if self.config["loss"]["iterative_mode"] not in _MODES:
+            raise IndexError("unknown iterative_mode %r" % (self.config["loss"]["iterative_mode"],))
+        return self._smoothing_terms(self._cm_loss())
+
+
+class Linear(BaseEventWarping):
+    """CM loss of Hagenaars and Paredes-Valles et al. (NeurIPS 2021) with linear warping
+    (upstream ``loss/flow.py:216-412``)."""
+
+    _linear = True
+
+    def update(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
+        self.update_base(flow_list)
+        self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
+        w = self._win
+        t = self._passes
+        P = self._max_passes()
+        F, B, H, W = w.shape
+        for k in range(2):
+            w.evflow[k].append(torch.empty((F, B, w.n[k][t], 2), dtype=torch.float32, device=w.packed.device))
+        if t < P:
+            # per-event flow is sampled now, from this pass' maps (:266-285)
+            d = self._desc_partial(w, t)
+            check(lib().tef_linear_sample(ctypes.byref(d), t, stream()), "tef_linear_sample")
+        self._passes += 1
+
+    def _desc_partial(self, w, t):
+        F, B, H, W = w.shape
+        d = CmDesc()
+        d.B, d.H, d.W, d.P, d.F = B, H, W, self._max_passes(), F
+        d.S = self.config["data"]["scales_loss"]
+        for k in range(2):
+            d.ev[k][t] = w.ev[k][t].data_ptr()
+            d.mk[k][t] = w.mk[k][t].data_ptr()
+            d.n[k][t] = w.n[k][t]
+            d.evflow[k][t] = w.evflow[k][t].data_ptr()
+        d.flow = w.packed.data_ptr()
+        return d
+
+    def forward(self):
+        return self._smoothing_terms(self._cm_loss())
+
+
+# BASELINE.json's north_star calls the loss "EventWarping"; upstream has no such class
+# (SURVEY.md §0).  The trained/default configuration is Iterative, mode "two".
+EventWarping = Iterative

@@ -1,0 +1,198 @@
+"""GPU parity of the fused CM losses (taming_event_flow_b200.loss.flow) against
+(a) the golden vectors made from the unmodified reference and (b) the CPU oracle on
+seeded synthetic streams.  Tolerances: 1e-5 norm-relative (L-inf and L2) for IWEs, loss and
+flow gradients, as BASELINE.json's north_star states; the per-event forward arithmetic
+is bit-faithful, so what remains is fp32 summation order."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cm_oracle as orc
+from taming_event_flow_b200 import synthetic as syn
+from util import load_loss_case, loss_case_names, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _module(kind, cfg, border=True, loss_scaling=True):
+    from taming_event_flow_b200.loss.flow import Iterative, Linear
+
+    cls = Iterative if kind == "iterative" else Linear
+    m = cls(cfg, "cuda", loss_scaling=loss_scaling)
+    m.border_compensation = border
+    return m
+
+
+def _run_gpu(kind, cfg, flows, events, masks, d_events, d_masks, border=True, loss_scaling=True, backward=True):
+    m = _module(kind, cfg, border, loss_scaling)
+    dev = torch.device("cuda")
+    fl = [[torch.as_tensor(f).to(dev).clone().requires_grad_(True) for f in per] for per in flows]
+    for t in range(len(fl)):
+        m.update(fl[t], torch.as_tensor(events[t]).to(dev).clone(), torch.as_tensor(masks[t]).to(dev).clone(),
+                 torch.as_tensor(d_events[t]).to(dev).clone(), torch.as_tensor(d_masks[t]).to(dev).clone())
+    loss = m()
+    img = m._win.img.detach().cpu().numpy().copy()          # [F,B,slots,H,W,(cnt+,ts+,cnt-,ts-)]
+    iwe = np.stack([img[..., 0], img[..., 2], img[..., 1], img[..., 3]], axis=3)   # -> [F,B,slots,4,H,W] oracle order
+    out = {"loss": float(loss.item()), "iwe": iwe, "module": m}
+    if backward:
+        loss.backward()
+        P, F = len(fl), len(fl[0])
+        out["gflow"] = np.stack([np.stack([fl[t][f].grad.cpu().numpy() for t in range(P)]) for f in range(F)])
+    return out
+
+
+def _cfg_for(c):
+    P_cfg = c["P"] // 2 if (c["mode"] == "four" and c["kind"] == "iterative") else c["P"]
+    return syn.loss_config(c["H"], c["W"], c["B"], P_cfg, c["S"], c["mode"])
+
+
+@pytest.mark.parametrize("name", loss_case_names())
+def test_golden_reference_parity(name):
+    c = load_loss_case(name)
+    g = _run_gpu(c["kind"], _cfg_for(c), c["flow_list"], c["events"], c["masks"], c["d_events"], c["d_masks"], border=bool(c["border"]))
+    assert abs(g["loss"] - c["loss32"]) <= TOL * abs(c["loss32"])
+    linf, l2 = rel_err(g["iwe"], c["iwe32"])
+    assert linf < TOL and l2 < TOL, ("iwe", linf, l2)
+    # which pixels hold events is an exact property (nnz of focus_loss)
+    assert np.array_equal(g["iwe"] != 0, c["iwe32"] != 0)
+    linf, l2 = rel_err(g["gflow"], c["grad32"])
+    assert linf < TOL and l2 < TOL, ("grad", linf, l2)
+    # triangulation against the fp64 run of the reference
+    e_gpu = rel_err(g["gflow"], c["grad64"])[1]
+    e_ref = rel_err(c["grad32"], c["grad64"])[1]
+    assert e_gpu <= 1.05 * e_ref + 1e-6
+
+
+CASES = [
+    # kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, dist
+    ("iterative", 8, 10, 2000, 2000, 128, 128, 1, 1, "two", 3.0, False, True, "uniform"),
+    ("iterative", 4, 10, 3000, 1000, 128, 128, 2, 1, "two", 0.5, True, True, "edges"),
+    ("iterative", 2, 8, 2500, 500, 96, 112, 1, 3, "two", 3.0, True, True, "uniform"),
+    ("iterative", 2, 8, 2000, 0, 64, 80, 1, 2, "one", 2.0, False, False, "uniform"),
+    ("iterative", 1, 10, 20000, 0, 480, 640, 1, 1, "two", 3.0, False, True, "uniform"),
+    ("iterative", 1, 24, 1500, 500, 64, 64, 1, 1, "two", 1.0, False, True, "uniform"),
+    ("linear", 8, 10, 2000, 2000, 128, 128, 2, 1, "two", 3.0, False, True, "uniform"),
+    ("linear", 2, 8, 3000, 1000, 96, 112, 1, 3, "two", 3.0, True, False, "edges"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-B%d-P%d-N%d+%d-%dx%d-F%d-S%d-%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9]))
+def test_oracle_parity_seeded(case):
+    kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, dist = case
+    seq = syn.make_sequence(11, B, P, N, Nd, H, W, F, sigma, ragged, dist)
+    cfg = syn.loss_config(H, W, B, P, S, mode)
+    g = _run_gpu(kind, cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], border=border)
+    oc = orc.make_cfg(B, H, W, P, F, S, mode, border)
+    fn = orc.iterative if kind == "iterative" else orc.linear
+    o = fn(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], np.float32, want_grad=True, want_iwe=True)
+    assert abs(g["loss"] - o["loss"]) <= TOL * abs(o["loss"])
+    linf, l2 = rel_err(g["iwe"], o["iwe"])
+    assert linf < TOL and l2 < TOL, ("iwe", linf, l2)
+    assert np.array_equal(g["iwe"] != 0, o["iwe"] != 0)
+    linf, l2 = rel_err(g["gflow"], o["gflow"])
+    assert linf < TOL and l2 < TOL, ("grad", linf, l2)
+
+
+def test_update_contract_and_reset():
+    """update() adds the pass index to the caller's timestamps in place (loss/flow.py:457-458), padding rows are inert,
+    reset() starts a fresh window, and a second window reproduces the first."""
+    B, P, N, H, W = 2, 4, 500, 32, 32
+    seq = syn.make_sequence(3, B, P, N, 100, H, W, 1, 2.0, ragged=True)
+    cfg = syn.loss_config(H, W, B, P)
+    m = _module("iterative", cfg)
+    losses = []
+    for rep in range(2):
+        for t in range(P):
+            ev = seq["events"][t].cuda().clone()
+            dev = seq["d_events"][t].cuda().clone()
+            m.update([f.cuda() for f in seq["flows"][t]], ev, seq["masks"][t].cuda(), dev, seq["d_masks"][t].cuda())
+            assert torch.equal(ev[:, :, 0].cpu(), seq["events"][t][:, :, 0] + t)
+            assert torch.equal(dev[:, :, 0].cpu(), seq["d_events"][t][:, :, 0] + t)
+            assert torch.equal(ev[:, :, 1:].cpu(), seq["events"][t][:, :, 1:])
+        assert m.num_passes == P
+        losses.append(m().item())
+        m.reset()
+        assert m.num_passes == 0
+    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
+    # extra zero rows (what custom_collate pads with) do not change the loss
+    m2 = _module("iterative", cfg)
+    for t in range(P):
+        ev = torch.cat([seq["events"][t], torch.zeros(B, 37, 4)], 1).cuda()
+        mk = torch.cat([seq["masks"][t], torch.zeros(B, 37, 2)], 1).cuda()
+        m2.update([f.cuda() for f in seq["flows"][t]], ev, mk, seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+    assert m2().item() == pytest.approx(losses[0], rel=1e-6)
+
+
+def test_errors_mirror_reference():
+    B, P, N, H, W = 1, 4, 100, 32, 32
+    seq = syn.make_sequence(5, B, P, N, 10, H, W, 1, 2.0)
+
+    def feed(m, n):
+        for t in range(n):
+            m.update([f.cuda() for f in seq["flows"][t]], seq["events"][t].cuda().clone(), seq["masks"][t].cuda(),
+                     seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+
+    m = _module("iterative", syn.loss_config(H, W, B, P))
+    feed(m, P - 1)
+    with pytest.raises(IndexError):        # too few passes
+        m()
+    m = _module("iterative", syn.loss_config(H, W, B, 1))
+    feed(m, 1)
+    with pytest.raises(RuntimeError):      # passes_loss=1, mode two -> delta 0 -> torch.cat([]) upstream
+        m()
+    cfg4 = syn.loss_config(H, W, B, 2, 1, "four")
+    m = _module("iterative", cfg4)
+    assert cfg4["data"]["passes_loss"] == 4   # the constructor doubles the caller's config (loss/flow.py:422-423)
+    feed(m, 4)
+    with pytest.raises(TypeError):         # mode four + border compensation
+        m()
+    # CPU tensors are refused: no fallback
+    from taming_event_flow_b200._lib import TefError
+    m = _module("iterative", syn.loss_config(H, W, B, P))
+    with pytest.raises(TefError):
+        m.update([f for f in seq["flows"][0]], seq["events"][0].clone(), seq["masks"][0], seq["d_events"][0].clone(), seq["d_masks"][0])
+
+
+def test_no_grad_and_double_backward():
+    B, P, N, H, W = 2, 4, 300, 32, 32
+    seq = syn.make_sequence(9, B, P, N, 50, H, W, 1, 2.0)
+    cfg = syn.loss_config(H, W, B, P)
+    m = _module("iterative", cfg)
+    flows = [[f.cuda().requires_grad_(True) for f in per] for per in seq["flows"]]
+    for t in range(P):
+        m.update(flows[t], seq["events"][t].cuda().clone(), seq["masks"][t].cuda(), seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+    with torch.no_grad():
+        l0 = m()
+    assert not l0.requires_grad
+    l1 = m()
+    assert l1.requires_grad and l1.item() == pytest.approx(l0.item(), rel=1e-6)
+    (2.0 * l1).backward(retain_graph=True)       # upstream gradient is honoured
+    g2 = flows[0][0].grad.clone()
+    with pytest.raises(RuntimeError):
+        l1.backward()
+    m.reset()
+    for t in range(P):
+        flows[t][0].grad = None
+        m.update(flows[t], seq["events"][t].cuda().clone(), seq["masks"][t].cuda(), seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+    m().backward()
+    assert rel_err(g2.cpu().numpy(), 2.0 * flows[0][0].grad.cpu().numpy())[0] < 1e-5
+
+
+def test_round_ts_and_loss_scaling_off():
+    B, P, N, H, W = 2, 4, 400, 32, 40
+    seq = syn.make_sequence(13, B, P, N, 100, H, W, 1, 2.0)
+    cfg = syn.loss_config(H, W, B, P, round_ts=True)
+    g = _run_gpu("iterative", cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
+    oc = orc.make_cfg(B, H, W, P, 1, 1, "two", True, True, round_ts=True)
+    o = orc.iterative(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
+    assert abs(g["loss"] - o["loss"]) <= TOL * abs(o["loss"])
+    assert rel_err(g["gflow"], o["gflow"])[0] < TOL
+    cfg = syn.loss_config(H, W, B, P)
+    g = _run_gpu("linear", cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], loss_scaling=False)
+    oc = orc.make_cfg(B, H, W, P, 1, 1, "two", True, loss_scaling=False)
+    o = orc.linear(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
+    assert abs(g["loss"] - o["loss"]) <= TOL * abs(o["loss"])
+    assert rel_err(g["gflow"], o["gflow"])[0] < TOL
