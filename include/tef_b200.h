@@ -112,9 +112,12 @@ int tef_get_interpolation_bwd(const float *warped, const float *g_w, float *g_wa
 /* interpolate (utils/iwe.py:116-136): iwe [B][H*W] must hold zeros or the `zeros` start image; pol may be NULL */
 int tef_interpolate(const float *idx, const float *w, const float *pol, float *iwe, int B, long M, int H, int W, void *stream);
 int tef_interpolate_bwd(const float *idx, const float *pol, const float *w, const float *g_iwe, float *g_w, float *g_pol, int B, long M, int H, int W, void *stream);
-/* deblur_events (utils/iwe.py:139-224): flow [B][2][H][W], events [B][N][4], pol [B][N] or NULL -> iwe [B][H*W] (zeroed inside) */
-int tef_deblur_events(const float *flow, const float *events, const float *pol, float *iwe, int B, int N, int H, int W,
-                      int round_idx, int round_flow, void *stream);
+/* deblur_events (utils/iwe.py:139-224), fused: flow [B][2][H][W], events [B][N][4]; pol may be NULL, else the
+   polarity of event i of the whole batch is pol[i * pol_stride] (a [B,N,2] mask column has stride 2);
+   sample b is accumulated into iwe + b * iwe_batch_stride (H*W floats, zeroed inside), so compute_pol_iwe
+   (utils/iwe.py:227-257) writes its two channels with two calls */
+int tef_deblur_events(const float *flow, const float *events, const float *pol, long pol_stride, float *iwe, long iwe_batch_stride,
+                      int B, int N, int H, int W, int round_idx, int round_flow, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* dataloader/encodings.py                                                    */

@@ -28,17 +28,15 @@ __device__ __forceinline__ bool inside(float y, float x, const Res &r) {
     return (y >= 0.0f) && (y <= (float)r.H - 1.0f) && (x >= 0.0f) && (x <= (float)r.W - 1.0f);
 }
 
-// bilinear flow sample = utils/iwe.py:17-40 + ATen grid_sampler_2d (zeros padding, align_corners=True)
-struct Taps {
+// bilinear sampling set-up = utils/iwe.py:17-40 (normalisation) + ATen grid_sampler_2d
+// (zeros padding, align_corners=True): tap indices, weights and fractional offsets.
+struct Bil {
     float w[4];       // nw, ne, sw, se
-    float2 v[4];      // tap values (.x = x-flow, .y = y-flow), 0 outside the map
     float ax, ay;     // fractional offsets along x / y
     int y0, x0;
     bool ok[4];
 };
-
-template <bool KEEP>
-__device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
+__device__ __forceinline__ void bilinear_setup(const Res &r, float y, float x, Bil &b) {
     float gy = (2.0f * y) / r.hm1 - 1.0f;          // utils/iwe.py:30
     float gx = (2.0f * x) / r.wm1 - 1.0f;          // utils/iwe.py:31
     float iy = (gy + 1.0f) * r.sh;                 // ATen unnormalize, align_corners=True
@@ -46,27 +44,42 @@ __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, co
     float fy0 = floorf(iy), fx0 = floorf(ix);
     float w_ = ix - fx0, e_ = 1.0f - w_;
     float n_ = iy - fy0, s_ = 1.0f - n_;
-    float wt[4] = { s_ * e_, s_ * w_, n_ * e_, n_ * w_ };
+    b.w[0] = s_ * e_; b.w[1] = s_ * w_; b.w[2] = n_ * e_; b.w[3] = n_ * w_;
+    b.ax = w_; b.ay = n_;
+    if (!(fx0 >= -2.0f && fx0 <= (float)(r.W + 1) && fy0 >= -2.0f && fy0 <= (float)(r.H + 1))) { b.y0 = -2; b.x0 = -2; }
+    else { b.y0 = (int)fy0; b.x0 = (int)fx0; }
+    const bool oy0 = (b.y0 >= 0) && (b.y0 < r.H), oy1 = (b.y0 + 1 >= 0) && (b.y0 + 1 < r.H);
+    const bool ox0 = (b.x0 >= 0) && (b.x0 < r.W), ox1 = (b.x0 + 1 >= 0) && (b.x0 + 1 < r.W);
+    b.ok[0] = oy0 && ox0; b.ok[1] = oy0 && ox1; b.ok[2] = oy1 && ox0; b.ok[3] = oy1 && ox1;
+}
+
+// sample of a packed (x-flow, y-flow) map; ATen accumulates nw*w0, fma(ne,w1,.), fma(sw,w2,.), fma(se,w3,.)
+struct Taps {
+    float w[4];
+    float2 v[4];      // tap values (.x = x-flow, .y = y-flow), 0 outside the map
+    float ax, ay;
     int y0, x0;
-    if (!(fx0 >= -2.0f && fx0 <= (float)(r.W + 1) && fy0 >= -2.0f && fy0 <= (float)(r.H + 1))) { y0 = -2; x0 = -2; }
-    else { y0 = (int)fy0; x0 = (int)fx0; }
-    const bool oy0 = (y0 >= 0) & (y0 < r.H), oy1 = (y0 + 1 >= 0) & (y0 + 1 < r.H);
-    const bool ox0 = (x0 >= 0) & (x0 < r.W), ox1 = (x0 + 1 >= 0) & (x0 + 1 < r.W);
-    const bool ok[4] = { oy0 && ox0, oy0 && ox1, oy1 && ox0, oy1 && ox1 };
-    const float2 *p = map + (long)y0 * r.W + x0;
+    bool ok[4];
+};
+
+template <bool KEEP>
+__device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
+    Bil b;
+    bilinear_setup(r, y, x, b);
+    const float2 *p = map + (long)b.y0 * r.W + b.x0;
     float2 v[4];
     const float2 z = make_float2(0.f, 0.f);
-    v[0] = ok[0] ? __ldg(p) : z;
-    v[1] = ok[1] ? __ldg(p + 1) : z;
-    v[2] = ok[2] ? __ldg(p + r.W) : z;
-    v[3] = ok[3] ? __ldg(p + r.W + 1) : z;
-    float ox = v[0].x * wt[0], oy = v[0].y * wt[0];
+    v[0] = b.ok[0] ? __ldg(p) : z;
+    v[1] = b.ok[1] ? __ldg(p + 1) : z;
+    v[2] = b.ok[2] ? __ldg(p + r.W) : z;
+    v[3] = b.ok[3] ? __ldg(p + r.W + 1) : z;
+    float ox = v[0].x * b.w[0], oy = v[0].y * b.w[0];
 #pragma unroll
-    for (int k = 1; k < 4; ++k) { ox = __fmaf_rn(v[k].x, wt[k], ox); oy = __fmaf_rn(v[k].y, wt[k], oy); }
+    for (int k = 1; k < 4; ++k) { ox = __fmaf_rn(v[k].x, b.w[k], ox); oy = __fmaf_rn(v[k].y, b.w[k], oy); }
     if (KEEP) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { tp->w[k] = wt[k]; tp->v[k] = v[k]; tp->ok[k] = ok[k]; }
-        tp->ax = w_; tp->ay = n_; tp->y0 = y0; tp->x0 = x0;
+        for (int k = 0; k < 4; ++k) { tp->w[k] = b.w[k]; tp->v[k] = v[k]; tp->ok[k] = b.ok[k]; }
+        tp->ax = b.ax; tp->ay = b.ay; tp->y0 = b.y0; tp->x0 = b.x0;
     }
     return make_float2(ox, oy);   // (.x = x-flow, .y = y-flow)
 }

@@ -1,0 +1,94 @@
+// tef_encodings.cu -- event encodings of the reference's dataloader/encodings.py as sm_100a kernels.
+// HBM-streaming kernels: 12-16 B read per event (coalesced), one or two native fp32 reductions into an
+// image that stays in L2.  Counting encodings are exact in fp32 for any order (integers < 2^24);
+// the voxel grid sums real weights, so only its summation order differs from the reference.
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+// xs.long()/ys.long() truncate toward zero; negative indices wrap like Python indexing (index_put_)
+__device__ __forceinline__ bool pixel_of(float xf, float yf, int H, int W, long &px) {
+    long x = (long)xf, y = (long)yf;
+    if (x < 0) x += W;
+    if (y < 0) y += H;
+    if (x < 0 || x >= W || y < 0 || y >= H) return false;          // the reference raises IndexError here
+    px = y * W + x;
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads) to_image_kernel(const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ ps,
+                                                            float *__restrict__ img, long n, int H, int W, int accumulate) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    long px;
+    if (!pixel_of(xs[i], ys[i], H, W, px)) return;
+    if (accumulate) red_add_f32(img + px, ps[i]);                   // dataloader/encodings.py:27
+    else img[px] = ps[i];
+}
+
+__global__ void __launch_bounds__(kThreads) to_channels_kernel(const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ ps,
+                                                               float *__restrict__ out, long n, int H, int W) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    long px;
+    if (!pixel_of(xs[i], ys[i], H, W, px)) return;
+    const float p = ps[i];
+    const float mpos = p < 0.f ? 0.f : (p > 0.f ? 1.f : p);        // :71-76
+    const float mneg = p > 0.f ? 0.f : (p < 0.f ? -1.f : p);
+    const float vp = p * mpos, vn = p * mneg;                       // :78-79
+    if (vp != 0.f) red_add_f32(out + px, vp);
+    if (vn != 0.f) red_add_f32(out + (long)H * W + px, vn);
+}
+
+__global__ void __launch_bounds__(kThreads) to_voxel_kernel(const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ ts,
+                                                            const float *__restrict__ ps, float *__restrict__ out, long n, int bins, int H, int W) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    long px;
+    if (!pixel_of(xs[i], ys[i], H, W, px)) return;
+    const float t = ts[i] * (float)(bins - 1);                      // :47
+    const float p = ps[i];
+    // only the bins within distance 1 of t have a non-zero weight (:52); the others add +0
+    int b0 = (int)floorf(t) - 1;
+    for (int b = max(b0, 0); b <= min(b0 + 3, bins - 1); ++b) {
+        const float wgt = fmaxf(0.0f, 1.0f - fabsf(t - (float)b));
+        const float v = p * wgt;                                    // :53
+        if (v != 0.f) red_add_f32(out + (long)b * H * W + px, v);
+    }
+}
+
+}  // namespace tef
+
+using namespace tef;
+#define ST ((cudaStream_t)stream)
+#define TEF_GRID(n) (unsigned)(((n) + kThreads - 1) / kThreads)
+
+extern "C" int tef_events_to_image(const float *xs, const float *ys, const float *ps, float *img, long n, int H, int W, int accumulate, void *stream) {
+    if (n < 0 || H < 1 || W < 1 || !img) return TEF_EINVAL;
+    cudaMemsetAsync(img, 0, sizeof(float) * (long)H * W, ST);
+    if (n == 0) return 0;
+    if (!xs || !ys || !ps) return TEF_EINVAL;
+    ProfScope pr(K_ENCODING, ST);
+    to_image_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(xs, ys, ps, img, n, H, W, accumulate);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, void *stream) {
+    if (n < 0 || H < 1 || W < 1 || !out) return TEF_EINVAL;
+    cudaMemsetAsync(out, 0, sizeof(float) * 2 * (long)H * W, ST);
+    if (n == 0) return 0;
+    if (!xs || !ys || !ps) return TEF_EINVAL;
+    ProfScope pr(K_ENCODING, ST);
+    to_channels_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(xs, ys, ps, out, n, H, W);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W,
+                                   void *stream) {
+    if (n < 0 || H < 1 || W < 1 || bins < 1 || !out) return TEF_EINVAL;
+    cudaMemsetAsync(out, 0, sizeof(float) * (long)bins * H * W, ST);
+    if (n == 0) return 0;
+    if (!xs || !ys || !ts || !ps) return TEF_EINVAL;
+    ProfScope pr(K_ENCODING, ST);
+    to_voxel_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(xs, ys, ts, ps, out, n, bins, H, W);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,51 @@
+"""Event encodings, drop-in for the reference's ``dataloader/encodings.py``.
+
+Same signatures as upstream (``dataloader/encodings.py:8-81``): 1-D coordinate / timestamp / polarity
+tensors in, image-like tensors out; each call is one CUDA kernel (one pass over the events, also
+for the voxel grid, where upstream makes ``num_bins`` passes).  Event counts are exact.
+"""
+import ctypes
+
+import torch
+
+from .._lib import check, lib, ptr, require_cuda, stream
+
+_l = ctypes.c_long
+
+
+def _prep(*ts):
+    require_cuda(*ts)
+    return [t.contiguous().float() for t in ts]
+
+
+def events_to_image(xs, ys, ps, sensor_size=(180, 240), accumulate=True):
+    """Accumulate events into an image (upstream ``dataloader/encodings.py:8-29``).
+
+    Coordinates are truncated like ``.long()``; negative ones wrap like Python indexing.  Events beyond the
+    sensor (where upstream raises ``IndexError``) are dropped.
+    """
+    xs, ys, ps = _prep(xs, ys, ps)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    img = torch.empty((H, W), dtype=torch.float32, device=xs.device)
+    check(lib().tef_events_to_image(ptr(xs), ptr(ys), ptr(ps), ptr(img), _l(xs.numel()), H, W, int(bool(accumulate)), stream()), "tef_events_to_image")
+    return img
+
+
+def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
+    """Voxel grid with temporal bilinear interpolation (upstream ``dataloader/encodings.py:32-56``): [num_bins x H x W]."""
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    xs, ys, ts, ps = _prep(xs, ys, ts, ps)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((int(num_bins), H, W), dtype=torch.float32, device=xs.device)
+    check(lib().tef_events_to_voxel(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(out), _l(xs.numel()), int(num_bins), H, W, stream()), "tef_events_to_voxel")
+    return out
+
+
+def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
+    """Two-channel per-polarity event counts (upstream ``dataloader/encodings.py:59-81``): [2 x H x W], both positive."""
+    assert len(xs) == len(ys) and len(ys) == len(ps)
+    xs, ys, ps = _prep(xs, ys, ps)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((2, H, W), dtype=torch.float32, device=xs.device)
+    check(lib().tef_events_to_channels(ptr(xs), ptr(ys), ptr(ps), ptr(out), _l(xs.numel()), H, W, stream()), "tef_events_to_channels")
+    return out

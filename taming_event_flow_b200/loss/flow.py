@@ -226,6 +226,31 @@ class BaseEventWarping(torch.nn.Module):
             loss = loss + self.flow_temporal_smoothing()
         return loss
 
+    # -------------------------------------------------- stand-alone pieces of the upstream API
+    def iwe_formatting(self, warped_events, pol_mask, ts_list, tref, ts_scaling, interp_zeros=None, iwe_zeros=None):
+        """Count and time-weighted images of warped events (upstream ``iwe_formatting``, loss/flow.py:81-110).
+
+        Kept for callers of the upstream method; `forward` does not go through it (the fused kernels
+        never materialise indices or weights)."""
+        from ..utils.iwe import get_interpolation, interpolate
+
+        norm_ts = 1 - torch.abs(tref - ts_list) / ts_scaling
+        idx, weights = get_interpolation(warped_events, self.res, zeros=interp_zeros)
+        iwe = torch.cat([interpolate(idx, weights, self.res, polarity_mask=pol_mask[:, :, c:c + 1], zeros=iwe_zeros) for c in range(2)], dim=1)
+        wts = weights * norm_ts
+        iwe_ts = torch.cat([interpolate(idx, wts, self.res, polarity_mask=pol_mask[:, :, c:c + 1], zeros=iwe_zeros) for c in range(2)], dim=1)
+        return iwe, iwe_ts
+
+    def focus_loss(self, iwe, iwe_ts):
+        """Sum of squared per-pixel average timestamps, scaled by the number of pixels with events
+        (upstream ``focus_loss``, loss/flow.py:112-129); summed over the batch."""
+        sq = iwe_ts.reshape(iwe_ts.shape[0], 2, -1) ** 2
+        loss = sq[:, 0].sum(1) + sq[:, 1].sum(1)
+        if self.loss_scaling:
+            nonzero = iwe.sum(1, keepdim=True).bool().reshape(iwe.shape[0], -1)
+            loss = loss / (nonzero.sum(1) + 1e-9)
+        return loss.sum()
+
     def flow_spatial_smoothing(self):
         raise NotImplementedError("flow_spat_smooth_weight is not None: the smoothness priors (upstream loss/flow.py:131-209) "
                                   "are outside the accelerated path (SURVEY.md §8f-3)")
@@ -271,7 +296,11 @@ class Linear(BaseEventWarping):
 
     _linear = True
 
+    def __init__(self, config, device, loss_scaling=True):
+        super().__init__(config, device, loss_scaling=loss_scaling)
+
     def update(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
+        """Same contract as upstream ``Linear.update`` (:233-288): flow is sampled per event right away."""
         self.update_base(flow_list)
         self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
         w = self._win

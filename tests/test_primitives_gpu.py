@@ -1,0 +1,171 @@
+"""GPU parity of the utils/iwe.py and dataloader/encodings.py drop-ins against the golden vectors made from
+the unmodified reference, and against the CPU oracle on larger seeded inputs.
+Per-event outputs (flow samples, positions, indices, weights) and event counts must be bit-exact;
+accumulated real-valued images within 1e-5 norm-relative (fp32 summation order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cm_oracle as orc
+from util import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def cu(a, grad=False):
+    t = torch.as_tensor(np.asarray(a)).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+@pytest.fixture(scope="module")
+def z():
+    return np.load(os.path.join(GOLDEN, "primitives.npz"))
+
+
+def test_get_event_flow_forward_backward(z):
+    from taming_event_flow_b200.utils.iwe import get_event_flow
+
+    mx, my, loc = cu(z["mapx"], True), cu(z["mapy"], True), cu(z["loc"], True)
+    out = get_event_flow(mx, my, loc)
+    assert np.array_equal(out.detach().cpu().numpy(), z["gef_out"])
+    out.backward(cu(z["gef_gout"]))
+    for got, ref in ((mx.grad, z["gef_gmapx"]), (my.grad, z["gef_gmapy"]), (loc.grad, z["gef_gloc"])):
+        linf, l2 = rel_err(got.cpu().numpy(), ref)
+        assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+def test_event_propagation_and_purge(z):
+    from taming_event_flow_b200.utils.iwe import event_propagation, purge_unfeasible
+
+    ts, loc, fl = cu(z["ts"], True), cu(z["loc"], True), cu(z["gef_out"], True)
+    out = event_propagation(ts, loc, fl, 1)
+    assert np.array_equal(out.detach().cpu().numpy(), z["prop_out"])
+    g = torch.randn_like(out)
+    out.backward(g)
+    ts2, loc2, fl2 = (t.detach().clone().requires_grad_(True) for t in (ts, loc, fl))
+    (loc2 + (1 - ts2) * fl2).backward(g)
+    for a, b in ((ts, ts2), (loc, loc2), (fl, fl2)):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy())[0] < 1e-6
+    res = (int(z["H"]), int(z["W"]))
+    pl, pm = purge_unfeasible(cu(z["loc"]), cu(z["mask"]), res)
+    assert np.array_equal(pl.cpu().numpy(), z["purge_loc"]) and np.array_equal(pm.cpu().numpy(), z["purge_mask"])
+    lg = cu(z["loc"], True)
+    pl, _ = purge_unfeasible(lg, cu(z["mask"]), res)
+    pl.sum().backward()
+    inside = (z["purge_loc"] != 0) | ((z["loc"] == 0) & True)
+    assert np.array_equal(lg.grad.cpu().numpy() != 0, np.broadcast_to(((z["loc"][..., 0:1] >= 0) & (z["loc"][..., 0:1] <= res[0] - 1) & (z["loc"][..., 1:2] >= 0) & (z["loc"][..., 1:2] <= res[1] - 1)), z["loc"].shape))
+
+
+def test_get_interpolation_forward_backward(z):
+    from taming_event_flow_b200.utils.iwe import get_interpolation
+
+    res = (int(z["H"]), int(z["W"]))
+    loc = cu(z["loc"], True)
+    idx, w = get_interpolation(loc, res)
+    assert np.array_equal(idx.cpu().numpy(), z["gi_idx"]) and np.array_equal(w.detach().cpu().numpy(), z["gi_w"])
+    w.backward(cu(z["gi_gw"]))
+    linf, l2 = rel_err(loc.grad.cpu().numpy(), z["gi_gloc"])      # includes the tie / integer-coordinate sub-gradients
+    assert linf < TOL and l2 < TOL, (linf, l2)
+    idx, w = get_interpolation(cu(z["loc"]), res, round_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), z["gi_ridx"]) and np.array_equal(w.cpu().numpy(), z["gi_rw"])
+
+
+def test_interpolate_forward_backward(z):
+    from taming_event_flow_b200.utils.iwe import interpolate
+
+    res = (int(z["H"]), int(z["W"]))
+    idx, w = cu(z["gi_idx"]), cu(z["gi_w"], True)
+    pol4 = cu(np.concatenate([z["mask"][:, :, 0:1]] * 4, 1))
+    for got, ref in ((interpolate(idx, w, res), z["interp_nopol"]), (interpolate(idx, w, res, polarity_mask=pol4), z["interp_pol"]),
+                     (interpolate(idx, w, res, polarity_mask=pol4, zeros=cu(z["interp_zeros_in"])), z["interp_zeros"])):
+        assert got.shape == ref.shape
+        linf, l2 = rel_err(got.detach().cpu().numpy(), ref)
+        assert linf < TOL and l2 < TOL
+    out = interpolate(idx, w, res, polarity_mask=pol4)
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref = torch.gather(g.view(g.shape[0], -1, 1), 1, idx.long()) * pol4
+    assert torch.equal(w.grad, ref)
+
+
+@pytest.mark.parametrize("ri", [True, False])
+@pytest.mark.parametrize("rf", [True, False])
+def test_compute_pol_iwe(z, ri, rf):
+    from taming_event_flow_b200.utils.iwe import compute_pol_iwe, deblur_events
+
+    res = (int(z["H"]), int(z["W"]))
+    ev = cu(z["db_ev_int"] if rf else z["db_ev_frac"])
+    out = compute_pol_iwe(cu(z["db_flow"]), ev, res, cu(z["mask"]), round_idx=ri, round_flow=rf)
+    ref = z["pol_iwe_ri%d_rf%d" % (ri, rf)]
+    assert out.shape == ref.shape
+    if ri:
+        assert np.array_equal(out.cpu().numpy(), ref)             # integer counts
+    else:
+        linf, l2 = rel_err(out.cpu().numpy(), ref)
+        assert linf < TOL and l2 < TOL
+    one = deblur_events(cu(z["db_flow"]), ev, res, round_idx=ri, polarity_mask=cu(z["mask"][:, :, 0:1]), round_flow=rf)
+    assert torch.equal(one[:, 0], out[:, 0])
+
+
+def test_iwe_formatting_and_focus_loss_match_fused_forward():
+    """The stand-alone upstream-style methods agree with the oracle's images for one reference time."""
+    from taming_event_flow_b200 import synthetic as syn
+    from taming_event_flow_b200.loss.flow import Iterative
+
+    B, N, H, W = 2, 3000, 40, 48
+    g = torch.Generator().manual_seed(5)
+    warped = torch.rand(B, N, 2, generator=g) * torch.tensor([H + 2.0, W + 2.0]) - 1.0
+    ts = torch.rand(B, N, 1, generator=g) * 4
+    p = (torch.randint(0, 2, (B, N), generator=g) * 2 - 1).float()
+    mask = torch.stack([(p > 0).float(), (p < 0).float()], -1)
+    m = Iterative(syn.loss_config(H, W, B, 4), "cuda")
+    iwe, iwe_ts = m.iwe_formatting(warped.cuda(), torch.cat([mask] * 4, 1).cuda(), torch.cat([ts] * 4, 1).cuda(), 2, 2)
+    idx, w = orc.get_interpolation(warped.numpy(), (H, W))
+    nts = (1 - np.abs(2 - np.concatenate([ts.numpy()] * 4, 1)) / 2).astype(np.float32)
+    for c in range(2):
+        pol = np.concatenate([mask.numpy()[:, :, c:c + 1]] * 4, 1)
+        assert rel_err(iwe[:, c:c + 1].cpu().numpy(), orc.interpolate(idx, w, (H, W), pol))[0] < TOL
+        assert rel_err(iwe_ts[:, c:c + 1].cpu().numpy(), orc.interpolate(idx, w * nts, (H, W), pol))[0] < TOL
+    a = iwe_ts / (iwe + 1e-9)
+    loss = m.focus_loss(iwe, a)
+    ref = 0.0
+    for b in range(B):
+        nz = (iwe[b].sum(0) != 0).sum().item()
+        ref += (a[b] ** 2).sum().item() / (nz + 1e-9)
+    assert loss.item() == pytest.approx(ref, rel=1e-5)
+
+
+def test_encodings_golden():
+    from taming_event_flow_b200.dataloader.encodings import events_to_channels, events_to_image, events_to_voxel
+
+    z = np.load(os.path.join(GOLDEN, "encodings.npz"))
+    ss = (int(z["H"]), int(z["W"]))
+    xs, ys, ts, ps = cu(z["xs"]), cu(z["ys"]), cu(z["ts"]), cu(z["ps"])
+    assert np.array_equal(events_to_image(xs, ys, ps, ss).cpu().numpy(), z["image"])            # +-1 sums: exact
+    assert np.array_equal(events_to_channels(xs, ys, ps, ss).cpu().numpy(), z["channels"])      # counts: bit-exact
+    v = events_to_voxel(xs, ys, ts, ps, int(z["bins"]), ss).cpu().numpy()
+    assert v.shape == z["voxel"].shape
+    linf, l2 = rel_err(v, z["voxel"])
+    assert linf < TOL and l2 < TOL
+    assert rel_err(v, z["voxel64"])[1] <= 1.05 * rel_err(z["voxel"], z["voxel64"])[1] + 1e-7
+
+
+@pytest.mark.parametrize("n", [0, 1, 1_000_000])
+def test_encodings_sizes(n):
+    from taming_event_flow_b200.dataloader.encodings import events_to_channels, events_to_voxel
+
+    H, W, bins = 480, 640, 5
+    g = torch.Generator().manual_seed(n)
+    xs = torch.randint(0, W, (n,), generator=g).float()
+    ys = torch.randint(0, H, (n,), generator=g).float()
+    ts = torch.rand(n, generator=g)
+    ps = (torch.randint(0, 2, (n,), generator=g) * 2 - 1).float()
+    ch = events_to_channels(xs.cuda(), ys.cuda(), ps.cuda(), (H, W)).cpu().numpy()
+    assert np.array_equal(ch, orc.events_to_channels(xs.numpy(), ys.numpy(), ps.numpy(), (H, W)))
+    assert ch.sum() == n                                                                           # a checksum of checksums
+    v = events_to_voxel(xs.cuda(), ys.cuda(), ts.cuda(), ps.cuda(), bins, (H, W)).cpu().numpy()
+    ref = orc.events_to_voxel(xs.numpy(), ys.numpy(), ts.numpy(), ps.numpy(), bins, (H, W))
+    assert rel_err(v, ref)[0] < TOL if n else not v.any()
