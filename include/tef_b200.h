@@ -52,8 +52,6 @@ typedef struct tef_cm_desc {
     const void *ev[2][TEF_MAX_PASSES];
     const void *mk[2][TEF_MAX_PASSES];
     int n[2][TEF_MAX_PASSES];
-    /* Linear only: per-event flow sampled at update time, float2 (y, x), [F][B*n] per pass */
-    void *evflow[2][TEF_MAX_PASSES];
     const void *flow;      /* packed flow maps, float2 (x, y): [F][P][B][H][W]         */
     void *gflow;           /* gradient of the packed maps, same layout (backward)      */
     void *img;             /* float4 (cnt+, ts+, cnt-, ts-) per pixel: [F][B][slots][H][W]; after backward
@@ -63,7 +61,17 @@ typedef struct tef_cm_desc {
     float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
     float *loss;           /* [1] scalar loss                                          */
     const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
+    /* workspace of the tile sort done by the forward calls (sizes from tef_cm_sort_workspace);
+       the backward reads sort_bins / sorted_ev / sorted_mk as the forward left them               */
+    void *sort_bins;       /* int [nbins + 1]                                          */
+    void *sort_sums;       /* int [nbins / 2048 + 1]                                   */
+    void *sorted_ev;       /* float4 [total rows]: (ts, y, x, sample index bits)       */
+    void *sorted_mk;       /* float2 [total rows]                                      */
 } tef_cm_desc;
+
+/* sizes of the sort workspace for the events currently described by `d`:
+   nbins (ints in sort_bins, +1), nsums (ints in sort_sums), rows (elements of sorted_ev / sorted_mk) */
+int tef_cm_sort_workspace(const tef_cm_desc *d, int linear, long *nbins, long *nsums, long *rows);
 
 /* number of image slots (scale, sub-window, tref) per (flow map, sample)             */
 int tef_cm_num_slots(const tef_cm_desc *d, int linear);
@@ -86,8 +94,8 @@ int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int
 int tef_iterative_forward(const tef_cm_desc *d, void *stream);
 int tef_iterative_backward(const tef_cm_desc *d, void *stream);
 
-/* Linear.update, flow part (loss/flow.py:266-285), Linear.forward (:306-412) and backward */
-int tef_linear_sample(const tef_cm_desc *d, int t, void *stream);
+/* Linear.forward (loss/flow.py:306-412) and backward; the per-event flow of Linear.update (:266-285)
+   is sampled inside the kernels from the packed map of the event's own pass */
 int tef_linear_forward(const tef_cm_desc *d, void *stream);
 int tef_linear_backward(const tef_cm_desc *d, void *stream);
 

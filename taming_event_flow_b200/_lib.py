@@ -37,7 +37,6 @@ class CmDesc(ctypes.Structure):
             ("ev", (ctypes.c_void_p * MAX_PASSES) * 2),
             ("mk", (ctypes.c_void_p * MAX_PASSES) * 2),
             ("n", (ctypes.c_int * MAX_PASSES) * 2),
-            ("evflow", (ctypes.c_void_p * MAX_PASSES) * 2),
             ("flow", ctypes.c_void_p),
             ("gflow", ctypes.c_void_p),
             ("img", ctypes.c_void_p),
@@ -46,6 +45,10 @@ class CmDesc(ctypes.Structure):
             ("den", ctypes.c_void_p),
             ("loss", ctypes.c_void_p),
             ("grad_out", ctypes.c_void_p),
+            ("sort_bins", ctypes.c_void_p),
+            ("sort_sums", ctypes.c_void_p),
+            ("sorted_ev", ctypes.c_void_p),
+            ("sorted_mk", ctypes.c_void_p),
         ]
     )
 

@@ -16,7 +16,17 @@ struct SegTable {
     int blk_off[kMaxSeg + 1];
     const float4 *ev[kMaxSeg];
     const float2 *mk[kMaxSeg];
-    float2 *evflow[kMaxSeg];
+    int first_bin[kMaxSeg + 1];      // first sort bin of the segment (bins are segment-major)
+};
+
+// geometry and buffers of the tile sort (tef_cm_sort.cu)
+struct SortGeom {
+    int B, H, W, tiles_x, tiles;     // 16x8-pixel tiles per sample
+    long nbins;                      // nseg * B * tiles * 128
+    int *bins;                       // [nbins + 1] histogram -> offsets -> bin ends
+    int *sums;                       // scan scratch, one int per 2048 bins
+    float4 *ev;                      // sorted rows (ts, y, x, sample index as int bits)
+    float2 *mk;
 };
 
 // One entry per temporal scale (loss/flow.py:42-44, :434-441, :657-668)
@@ -41,6 +51,7 @@ struct CmParams {
     const float *grad_out;
     SegTable seg;
     ScaleTable sc;
+    SortGeom sort;
 };
 
 // slot -> scale / divisor tables for the reduction kernels (few entries, in constant param space)
@@ -76,7 +87,7 @@ inline int check_desc(const tef_cm_desc *d, int linear) {
     return 0;
 }
 
-inline int fill_params(const tef_cm_desc *d, int linear, bool grad_only, CmParams &p) {
+inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     int rc = check_desc(d, linear);
     if (rc) return rc;
     p.B = d->B; p.H = d->H; p.W = d->W; p.P = d->P; p.F = d->F; p.mode = d->mode;
@@ -86,20 +97,56 @@ inline int fill_params(const tef_cm_desc *d, int linear, bool grad_only, CmParam
     p.acc_sum = d->acc_sum; p.acc_nnz = d->acc_nnz; p.den = d->den; p.loss = d->loss; p.grad_out = d->grad_out;
     p.nslots = build_scales(d, linear, p.sc);
     int ns = 0, blk = 0;
-    for (int set = 0; set < (grad_only ? 1 : 2); ++set)
+    for (int set = 0; set < 2; ++set)
         for (int t = 0; t < d->P; ++t) {
             if (d->n[set][t] <= 0) continue;
             if (!d->ev[set][t] || !d->mk[set][t]) return TEF_EINVAL;
             p.seg.set[ns] = set; p.seg.pass[ns] = t; p.seg.n[ns] = d->n[set][t];
             p.seg.ev[ns] = (const float4 *)d->ev[set][t]; p.seg.mk[ns] = (const float2 *)d->mk[set][t];
-            p.seg.evflow[ns] = (float2 *)d->evflow[set][t];
             p.seg.blk_off[ns] = blk;
             long rows = (long)d->B * d->n[set][t];
             blk += (int)((rows + kThreads - 1) / kThreads);
             ++ns;
         }
     p.seg.nseg = ns; p.seg.blk_off[ns] = blk;
+    SortGeom &g = p.sort;
+    g.B = d->B; g.H = d->H; g.W = d->W;
+    g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
+    for (int s = 0; s <= ns; ++s) p.seg.first_bin[s] = s * d->B * g.tiles * 128;
+    g.nbins = (long)ns * d->B * g.tiles * 128;
+    g.bins = (int *)d->sort_bins; g.sums = (int *)d->sort_sums;
+    g.ev = (float4 *)d->sorted_ev; g.mk = (float2 *)d->sorted_mk;
     return 0;
+}
+
+// the backward only visits the gradient-carrying set; its segments come first
+inline void grad_segments_only(CmParams &p) {
+    int ng = 0;
+    while (ng < p.seg.nseg && p.seg.set[ng] == 0) ++ng;
+    p.seg.nseg = ng;
+}
+
+// rows of segment sg in the sorted arrays: [lo, hi)
+__device__ __forceinline__ void seg_rows(const CmParams &p, int sg, int &lo, int &hi) {
+    const int fb = p.seg.first_bin[sg];
+    lo = fb ? __ldg(p.sort.bins + fb - 1) : 0;
+    hi = __ldg(p.sort.bins + p.seg.first_bin[sg + 1] - 1);
+}
+
+// CTA -> segment, thread -> sorted row; false when the thread has no event
+__device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b, float4 &e, float2 &m) {
+    int sg = 0;
+    const int blk = blockIdx.x;
+    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
+    t = p.seg.pass[sg];
+    int lo, hi;
+    seg_rows(p, sg, lo, hi);
+    const int row = lo + (blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    if (row >= hi) return false;
+    e = __ldg(p.sort.ev + row);
+    m = __ldg(p.sort.mk + row);
+    b = __float_as_int(e.w);
+    return true;
 }
 
 // upstream gradient of one focus_loss value, divided in the order autograd unwinds

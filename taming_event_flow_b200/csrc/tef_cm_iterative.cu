@@ -91,16 +91,9 @@ __device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
 
 __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
-    int sg = 0;
-    const int blk = blockIdx.x;
-    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
-    const int n = p.seg.n[sg], t = p.seg.pass[sg];
-    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
-    if (row >= (long)p.B * n) return;
-    const float2 m = __ldg(p.seg.mk[sg] + row);
-    if (m.x == 0.0f && m.y == 0.0f) return;        // padding rows contribute nothing
-    const float4 e = __ldg(p.seg.ev[sg] + row);
-    const int b = (int)(row / n), f = blockIdx.y;
+    int t, b; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m)) return;
+    const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
 
@@ -143,16 +136,9 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
 
 __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
-    int sg = 0;
-    const int blk = blockIdx.x;
-    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
-    const int n = p.seg.n[sg], t = p.seg.pass[sg];
-    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
-    if (row >= (long)p.B * n) return;
-    const float2 m = __ldg(p.seg.mk[sg] + row);
-    if (m.x == 0.0f && m.y == 0.0f) return;
-    const float4 e = __ldg(p.seg.ev[sg] + row);
-    const int b = (int)(row / n), f = blockIdx.y;
+    int t, b; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m)) return;
+    const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
     float2 *gflow_f = p.gflow + (long)f * p.P * p.B * HW;
@@ -223,6 +209,7 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------
 using namespace tef;
 
+int tef_sort_events(const CmParams &p, cudaStream_t st);           // tef_cm_sort.cu
 int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st);   // tef_cm_reduce.cu
 int tef_grad_images(const CmParams &p, cudaStream_t st);           // tef_cm_reduce.cu
 
@@ -252,12 +239,14 @@ static int launch_bwd(const CmParams &p, cudaStream_t st) {
 extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CmParams p;
-    int rc = fill_params(d, 0, false, p);
+    int rc = fill_params(d, 0, p);
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
     const long HW = (long)p.H * p.W;
     const long nimg = (long)p.F * p.B * p.nslots;
     cudaMemsetAsync(p.img, 0, sizeof(float4) * nimg * HW, st);
+    rc = tef_sort_events(p, st);
+    if (rc) return rc;
     rc = launch_fwd(p, st);
     if (rc) return rc;
     return tef_reduce_and_finalize(p, st);
@@ -266,9 +255,10 @@ extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
 extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CmParams p;
-    int rc = fill_params(d, 0, true, p);
+    int rc = fill_params(d, 0, p);                 // same segment / bin layout as the forward call
     if (rc) return rc;
-    if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out) return TEF_EINVAL;
+    if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.ev || !p.sort.mk) return TEF_EINVAL;
+    grad_segments_only(p);
     const long HW = (long)p.H * p.W;
     cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * HW, st);
     rc = tef_grad_images(p, st);

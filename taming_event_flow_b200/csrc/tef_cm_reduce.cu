@@ -125,3 +125,15 @@ extern "C" int tef_cm_num_slots(const tef_cm_desc *d, int linear) {
     ScaleTable sc;
     return build_scales(d, linear, sc);
 }
+
+extern "C" int tef_cm_sort_workspace(const tef_cm_desc *d, int linear, long *nbins, long *nsums, long *rows) {
+    CmParams p;
+    int rc = fill_params(d, linear, p);
+    if (rc) return rc;
+    long r = 0;
+    for (int s = 0; s < p.seg.nseg; ++s) r += (long)p.B * p.seg.n[s];
+    if (nbins) *nbins = p.sort.nbins + 1;
+    if (nsums) *nsums = p.sort.nbins / 2048 + 2;
+    if (rows) *rows = r;
+    return 0;
+}

@@ -1,0 +1,131 @@
+// tef_cm_sort.cu -- device counting sort of the staged events by pixel tile.
+//
+// Why: with events in arrival (time) order every bilinear gather and every image reduction of a warp
+// touches ~32 different L2 sectors, and both loss kernels saturate the L1/L2 transaction rate
+// (profiles/r1_a_*: 30.7 sectors per load request, 15.4 per RED request, L1 hit 21 %).  The loss is a sum
+// over events, so their order is free: sorting each (set, pass) segment by (sample, 16x8-pixel tile, pixel)
+// makes the lanes of a warp start from the same few pixels and, the flow being smooth, stay neighbours
+// along the whole warping chain.  Padding rows (mask 0,0) are dropped on the way.
+//
+// Three steps, all inside tef_*_forward:  histogram over per-pixel bins (1 L2 atomic per event),
+// exclusive scan of the bins, scatter (1 returning atomic per event).  Output rows carry the sample
+// index in the 4th float (the polarity column is not needed by the loss; the mask carries it).
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+__device__ __forceinline__ int bin_of(const SortGeom &g, int seg, int b, float y, float x) {
+    int iy = (int)fminf(fmaxf(floorf(y), 0.0f), (float)(g.H - 1));
+    int ix = (int)fminf(fmaxf(floorf(x), 0.0f), (float)(g.W - 1));
+    const int tile = (iy >> 3) * g.tiles_x + (ix >> 4);
+    return ((seg * g.B + b) * g.tiles + tile) * 128 + ((iy & 7) << 4) + (ix & 15);
+}
+
+__global__ void __launch_bounds__(kThreads) sort_hist_kernel(const __grid_constant__ CmParams p) {
+    int sg = 0;
+    const int blk = blockIdx.x;
+    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
+    const int n = p.seg.n[sg];
+    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    if (row >= (long)p.B * n) return;
+    const float2 m = __ldg(p.seg.mk[sg] + row);
+    if (m.x == 0.0f && m.y == 0.0f) return;        // padding rows are dropped
+    const float4 e = __ldg(p.seg.ev[sg] + row);
+    atomicAdd(p.sort.bins + bin_of(p.sort, sg, (int)(row / n), e.y, e.z), 1);
+}
+
+__global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const __grid_constant__ CmParams p) {
+    int sg = 0;
+    const int blk = blockIdx.x;
+    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
+    const int n = p.seg.n[sg];
+    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    if (row >= (long)p.B * n) return;
+    const float2 m = __ldg(p.seg.mk[sg] + row);
+    if (m.x == 0.0f && m.y == 0.0f) return;
+    float4 e = __ldg(p.seg.ev[sg] + row);
+    const int b = (int)(row / n);
+    const int dst = atomicAdd(p.sort.bins + bin_of(p.sort, sg, b, e.y, e.z), 1);
+    e.w = __int_as_float(b);
+    p.sort.ev[dst] = e;
+    p.sort.mk[dst] = m;
+}
+
+// ---- exclusive scan of the bins (int), three small kernels ------------------------------------------
+constexpr int kScanChunk = 2048;     // elements per CTA (8 per thread)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[kThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < kThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane < kThreads / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[kThreads / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_sums_kernel(const int *__restrict__ bins, int *__restrict__ sums, long nbins) {
+    const long base = (long)blockIdx.x * kScanChunk + threadIdx.x * 8;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (base + k < nbins) s += bins[base + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ int ws[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < kThreads / 32; ++k) t += ws[k]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(kThreads) scan_top_kernel(int *__restrict__ sums, int nsums) {
+    int carry = 0;
+    for (int base = 0; base < nsums; base += kThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < nsums ? sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (i < nsums) sums[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(int *__restrict__ bins, const int *__restrict__ sums, long nbins) {
+    const long base = (long)blockIdx.x * kScanChunk + threadIdx.x * 8;
+    int v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = (base + k < nbins) ? bins[base + k] : 0; s += v[k]; }
+    int run = block_exclusive_scan(s, nullptr) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (base + k < nbins) bins[base + k] = run; run += v[k]; }
+}
+
+}  // namespace tef
+
+using namespace tef;
+
+// Sort every segment of `p` (as laid out by fill_params) into p.sort.ev / p.sort.mk.  Afterwards
+// bins[i] holds the END of bin i, so segment s occupies rows [bins[first_bin(s)-1] (or 0), bins[last_bin(s)]).
+int tef_sort_events(const CmParams &p, cudaStream_t st) {
+    const int nblk = p.seg.blk_off[p.seg.nseg];
+    const long nbins = p.sort.nbins;
+    if (!p.sort.bins || !p.sort.sums || (nblk > 0 && (!p.sort.ev || !p.sort.mk))) return TEF_EINVAL;
+    cudaMemsetAsync(p.sort.bins, 0, sizeof(int) * (nbins + 1), st);
+    if (nblk == 0) return (int)cudaGetLastError();
+    const int nchunks = (int)((nbins + kScanChunk - 1) / kScanChunk);
+    { ProfScope ps(K_SORT_HIST, st); sort_hist_kernel<<<nblk, kThreads, 0, st>>>(p); }
+    { ProfScope ps(K_SORT_SCAN, st); scan_sums_kernel<<<nchunks, kThreads, 0, st>>>(p.sort.bins, p.sort.sums, nbins); }
+    { ProfScope ps(K_SORT_SCAN, st); scan_top_kernel<<<1, kThreads, 0, st>>>(p.sort.sums, nchunks); }
+    { ProfScope ps(K_SORT_SCAN, st); scan_apply_kernel<<<nchunks, kThreads, 0, st>>>(p.sort.bins, p.sort.sums, nbins); }
+    { ProfScope ps(K_SORT_SCATTER, st); sort_scatter_kernel<<<nblk, kThreads, 0, st>>>(p); }
+    return (int)cudaGetLastError();
+}

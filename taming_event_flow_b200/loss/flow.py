@@ -29,7 +29,7 @@ class _Window:
         self.ev = ([], [])     # staged events per pass, (grad set, detached set)
         self.mk = ([], [])
         self.n = ([], [])
-        self.evflow = ([], []) # Linear only
+        self.sort = None       # (bins, sums, sorted_ev, sorted_mk), written by the forward kernels
         self.shape = None      # (F, B, H, W)
         self.img = None
         self.den = None
@@ -168,9 +168,9 @@ class BaseEventWarping(torch.nn.Module):
                 d.ev[k][t] = w.ev[k][t].data_ptr()
                 d.mk[k][t] = w.mk[k][t].data_ptr()
                 d.n[k][t] = w.n[k][t]
-                if self._linear:
-                    d.evflow[k][t] = w.evflow[k][t].data_ptr()
         d.flow = w.packed.data_ptr()
+        if w.sort is not None:
+            d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk = (x.data_ptr() for x in w.sort)
         return d
 
     def _forward_kernels(self, w):
@@ -179,6 +179,13 @@ class BaseEventWarping(torch.nn.Module):
         nslots = lib().tef_cm_num_slots(ctypes.byref(d), int(self._linear))
         check(min(nslots, 0), "tef_cm_num_slots")
         dev = w.packed.device
+        nb, nsum, rows = ctypes.c_long(), ctypes.c_long(), ctypes.c_long()
+        check(lib().tef_cm_sort_workspace(ctypes.byref(d), int(self._linear), ctypes.byref(nb), ctypes.byref(nsum), ctypes.byref(rows)),
+              "tef_cm_sort_workspace")
+        w.sort = (torch.empty((nb.value,), dtype=torch.int32, device=dev), torch.empty((nsum.value,), dtype=torch.int32, device=dev),
+                  torch.empty((max(rows.value, 1), 4), dtype=torch.float32, device=dev),
+                  torch.empty((max(rows.value, 1), 2), dtype=torch.float32, device=dev))
+        d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk = (x.data_ptr() for x in w.sort)
         w.img = torch.empty((F, B, nslots, H, W, 4), dtype=torch.float32, device=dev)
         w.acc_sum = torch.empty((F, B, nslots), dtype=torch.float64, device=dev)
         w.acc_nnz = torch.empty((F, B, nslots), dtype=torch.int32, device=dev)
@@ -300,33 +307,11 @@ class Linear(BaseEventWarping):
         super().__init__(config, device, loss_scaling=loss_scaling)
 
     def update(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
-        """Same contract as upstream ``Linear.update`` (:233-288): flow is sampled per event right away."""
+        """Same contract as upstream ``Linear.update`` (:233-288).  Upstream samples the per-event flow here; the
+        kernels sample the same values from this pass' packed map inside `forward`."""
         self.update_base(flow_list)
         self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
-        w = self._win
-        t = self._passes
-        P = self._max_passes()
-        F, B, H, W = w.shape
-        for k in range(2):
-            w.evflow[k].append(torch.empty((F, B, w.n[k][t], 2), dtype=torch.float32, device=w.packed.device))
-        if t < P:
-            # per-event flow is sampled now, from this pass' maps (:266-285)
-            d = self._desc_partial(w, t)
-            check(lib().tef_linear_sample(ctypes.byref(d), t, stream()), "tef_linear_sample")
         self._passes += 1
-
-    def _desc_partial(self, w, t):
-        F, B, H, W = w.shape
-        d = CmDesc()
-        d.B, d.H, d.W, d.P, d.F = B, H, W, self._max_passes(), F
-        d.S = self.config["data"]["scales_loss"]
-        for k in range(2):
-            d.ev[k][t] = w.ev[k][t].data_ptr()
-            d.mk[k][t] = w.mk[k][t].data_ptr()
-            d.n[k][t] = w.n[k][t]
-            d.evflow[k][t] = w.evflow[k][t].data_ptr()
-        d.flow = w.packed.data_ptr()
-        return d
 
     def forward(self):
         return self._smoothing_terms(self._cm_loss())

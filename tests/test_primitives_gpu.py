@@ -107,7 +107,10 @@ def test_compute_pol_iwe(z, ri, rf):
         linf, l2 = rel_err(out.cpu().numpy(), ref)
         assert linf < TOL and l2 < TOL
     one = deblur_events(cu(z["db_flow"]), ev, res, round_idx=ri, polarity_mask=cu(z["mask"][:, :, 0:1]), round_flow=rf)
-    assert torch.equal(one[:, 0], out[:, 0])
+    if ri:
+        assert torch.equal(one[:, 0], out[:, 0])
+    else:                                                            # two launches: fp32 summation order differs
+        assert rel_err(one[:, 0].cpu().numpy(), out[:, 0].cpu().numpy())[0] < TOL
 
 
 def test_iwe_formatting_and_focus_loss_match_fused_forward():
