@@ -53,28 +53,28 @@ typedef struct tef_cm_desc {
     const void *mk[2][TEF_MAX_PASSES];
     int n[2][TEF_MAX_PASSES];
     const void *flow;      /* packed flow maps, float2 (x, y): [F][P][B][H][W]         */
-    void *gflow;           /* gradient of the packed maps, same layout (backward)      */
-    void *img;             /* float4 (cnt+, ts+, cnt-, ts-) per pixel: [F][B][slots][H][W]; after backward
-                              it holds the gradient images (dL/dcnt+, dL/dts+, dL/dcnt-, dL/dts-)         */
+    void *gflow;           /* gradient of the packed maps, dual-phase: [F][P][B][phase][H][Wp] float2 (backward) */
+    void *img;             /* accumulation images, float2 (count, time-weighted): [F][B][slots][phase][pol][H][Wp];
+                              pixel x lives at column x of phase 0 plus column x+1 of phase 1 (see csrc/tef_cm_common.cuh);
+                              after backward the phase-0 planes hold (dL/dcount, dL/dtime-weighted)              */
     double *acc_sum;       /* [F][B][slots] sum of squared normalised timestamps       */
     int *acc_nnz;          /* [F][B][slots] pixels with at least one event             */
     float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
     float *loss;           /* [1] scalar loss                                          */
     const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
-    /* workspace of the tile sort done by the forward calls (sizes from tef_cm_sort_workspace);
-       the backward reads sort_bins / sorted_ev / sorted_mk as the forward left them               */
-    void *sort_bins;       /* int [nbins + 1]                                          */
-    void *sort_sums;       /* int [nbins / 2048 + 1]                                   */
-    void *sorted_ev;       /* float4 [total rows]: (ts, y, x, sample index bits)       */
-    void *sorted_mk;       /* float2 [total rows]                                      */
+    /* workspace written by the forward call and read by the backward call (sizes from tef_cm_sizes) */
+    void *sort_bins;       /* int [nbins + 1]  tile-sort histogram / offsets           */
+    void *sort_sums;       /* int scan scratch                                         */
+    void *sorted_ev;       /* float4 [rows]: (ts, y, x, sample index bits), tile-sorted */
+    void *sorted_mk;       /* float2 [rows]                                            */
+    void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
+    void *alivebuf;        /* uint64 [F][rows_grad] cumulative in-image bits           */
 } tef_cm_desc;
 
-/* sizes of the sort workspace for the events currently described by `d`:
-   nbins (ints in sort_bins, +1), nsums (ints in sort_sums), rows (elements of sorted_ev / sorted_mk) */
-int tef_cm_sort_workspace(const tef_cm_desc *d, int linear, long *nbins, long *nsums, long *rows);
-
-/* number of image slots (scale, sub-window, tref) per (flow map, sample)             */
-int tef_cm_num_slots(const tef_cm_desc *d, int linear);
+/* buffer sizes for the events currently described by `d`; out[9] =
+   { slots, floats in img, floats in gflow, ints in sort_bins, ints in sort_sums, rows of sorted_ev/sorted_mk,
+     gradient-carrying rows, floats in posbuf, padded row length Wp } */
+int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out);
 
 /* Iterative.update / Linear.update, event part (loss/flow.py:456-473, :246-263):
    ts += pass_index IN PLACE in the caller's [B,n,4] tensor, then (ts | ts_override), y, x, p

@@ -49,6 +49,8 @@ class CmDesc(ctypes.Structure):
             ("sort_sums", ctypes.c_void_p),
             ("sorted_ev", ctypes.c_void_p),
             ("sorted_mk", ctypes.c_void_p),
+            ("posbuf", ctypes.c_void_p),
+            ("alivebuf", ctypes.c_void_p),
         ]
     )
 
@@ -114,7 +116,7 @@ def ptr(t):
 def stream():
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def require_cuda(*tensors):

@@ -38,12 +38,27 @@ struct ScaleTable {
     int ntau[TEF_MAX_SCALES];       // reference times per sub-window (Linear: 2)
 };
 
+// Accumulation images are polarity-planar float2 (count, time-weighted count) with rows padded to Wp and
+// stored twice ("phases"): phase 0 holds pixel x at column x, phase 1 at column x+1.  A horizontally adjacent
+// corner pair (x0, x0+1) is therefore always one 16-byte aligned float4 in the phase x0&1, and goes out as a
+// single red.global.add.v4.f32 -- half the reduction lane-ops of per-corner updates.  The two phases are
+// summed when the image is read.  Layout: [F][B][slot][phase][pol][H][Wp] float2.
+// The packed flow gradient uses the same trick: [F][P][B][phase][H][Wp] float2 (d/dx-flow, d/dy-flow).
+struct ImgGeom {
+    int Wp;          // padded row length (even, >= W + 2)
+    long plane;      // H * Wp
+};
+
 struct CmParams {
     int B, H, W, P, F, mode, border, loss_scaling, nslots, linear;
     Res res;
+    ImgGeom ig;
     const float2 *flow;
     float2 *gflow;
-    float4 *img;
+    float2 *img;
+    float2 *posbuf;          // [(P+1)][rows_grad] chain positions of the gradient-carrying rows (Iterative)
+    unsigned long long *alivebuf;   // [rows_grad]
+    long rows_grad;
     double *acc_sum;
     int *acc_nnz;
     float *den;
@@ -93,7 +108,9 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     p.B = d->B; p.H = d->H; p.W = d->W; p.P = d->P; p.F = d->F; p.mode = d->mode;
     p.border = d->border_comp; p.loss_scaling = d->loss_scaling; p.linear = linear;
     p.res = Res::make(d->H, d->W);
-    p.flow = (const float2 *)d->flow; p.gflow = (float2 *)d->gflow; p.img = (float4 *)d->img;
+    p.flow = (const float2 *)d->flow; p.gflow = (float2 *)d->gflow; p.img = (float2 *)d->img;
+    p.ig.Wp = (d->W + 3) & ~1; p.ig.plane = (long)d->H * p.ig.Wp;
+    p.posbuf = (float2 *)d->posbuf; p.alivebuf = (unsigned long long *)d->alivebuf;
     p.acc_sum = d->acc_sum; p.acc_nnz = d->acc_nnz; p.den = d->den; p.loss = d->loss; p.grad_out = d->grad_out;
     p.nslots = build_scales(d, linear, p.sc);
     int ns = 0, blk = 0;
@@ -109,6 +126,8 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
             ++ns;
         }
     p.seg.nseg = ns; p.seg.blk_off[ns] = blk;
+    p.rows_grad = 0;
+    for (int t = 0; t < d->P; ++t) p.rows_grad += (long)d->B * (d->n[0][t] > 0 ? d->n[0][t] : 0);
     SortGeom &g = p.sort;
     g.B = d->B; g.H = d->H; g.W = d->W;
     g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
@@ -134,14 +153,14 @@ __device__ __forceinline__ void seg_rows(const CmParams &p, int sg, int &lo, int
 }
 
 // CTA -> segment, thread -> sorted row; false when the thread has no event
-__device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b, float4 &e, float2 &m) {
+__device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b, float4 &e, float2 &m, int &row, int &set) {
     int sg = 0;
     const int blk = blockIdx.x;
     while (blk >= p.seg.blk_off[sg + 1]) ++sg;
-    t = p.seg.pass[sg];
+    t = p.seg.pass[sg]; set = p.seg.set[sg];
     int lo, hi;
     seg_rows(p, sg, lo, hi);
-    const int row = lo + (blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
+    row = lo + (blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
     if (row >= hi) return false;
     e = __ldg(p.sort.ev + row);
     m = __ldg(p.sort.mk + row);
@@ -160,40 +179,77 @@ __host__ __device__ inline float upstream(float gout, int F, int S, float div_a,
     return g;
 }
 
-// iwe_formatting (loss/flow.py:81-110) for one event: 4 corners x (count, time-weighted) of its polarity
-__device__ __forceinline__ void splat(float4 *__restrict__ im, const Res &r, float y, float x, float nts, float2 m) {
-    Corners c;
-    corners(y, x, r, c);
-#pragma unroll
-    for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 2; ++kx) {
-            if (!(c.oky[ky] && c.okx[kx])) continue;
-            const float w = c.wy[ky] * c.wx[kx];
-            if (w == 0.0f) continue;
-            const float wt = w * nts;
-            float2 *dst = reinterpret_cast<float2 *>(im + ((long)c.cy[ky] * r.W + (long)c.cx[kx]));
-            if (m.x != 0.0f) red_add_v2(dst, w * m.x, wt * m.x);
-            if (m.y != 0.0f) red_add_v2(dst + 1, w * m.y, wt * m.y);
-        }
+__device__ __forceinline__ void red_add_v4(float2 *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// gradient of the loss w.r.t. the position at one reference time, through the bilinear
-// splat weights; im holds the gradient images.
-__device__ __forceinline__ void iwe_grad(const float4 *__restrict__ im, const Res &r, float y, float x, float nts, float2 m,
-                                         float &gy, float &gx) {
+// planes of one image slot: [phase][pol]
+__device__ __forceinline__ float2 *img_plane(float2 *slot_base, const ImgGeom &g, int phase, int pol) {
+    return slot_base + (long)(phase * 2 + pol) * g.plane;
+}
+
+// iwe_formatting (loss/flow.py:81-110) for one event: per image row one 16-byte reduction carrying
+// (w_left, w_left*n, w_right, w_right*n) into the plane of the event's polarity.
+// Corner coordinates, weights and in-image tests are exactly get_interpolation's (utils/iwe.py:85-107);
+// a corner outside the image (or with weight 0) contributes an exact +0.
+__device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts, float2 m) {
     Corners c;
     corners(y, x, r, c);
+    if (!(c.okx[0] || c.okx[1])) return;
+    const int xl = c.okx[0] ? (int)c.cx[0] : (int)c.cx[1] - 1;      // column of the left corner (-1 .. W-1)
+    const int phase = xl & 1;
+    const int col = xl + phase;                                     // even -> 16-byte aligned pair
+    const int pol = (m.x != 0.0f) ? 0 : 1;
+    const float mv = pol ? m.y : m.x;
+    const bool both = (m.x != 0.0f) && (m.y != 0.0f);               // non-binary masks only
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        if (!c.oky[ky]) continue;
+        const float wl = c.okx[0] ? c.wy[ky] * c.wx[0] : 0.0f;
+        const float wr = c.okx[1] ? c.wy[ky] * c.wx[1] : 0.0f;
+        if (wl == 0.0f && wr == 0.0f) continue;
+        const long off = (long)c.cy[ky] * g.Wp + col;
+        const float tl = wl * nts, tr = wr * nts;
+        red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
+        if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
+    }
+}
+
+// gradient of the loss w.r.t. the position at one reference time, through the bilinear splat weights
+// (SURVEY.md Appendix A.4); the gradient images (dL/dcount, dL/dtime-weighted) live in the phase-0 planes.
+__device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts,
+                                         float2 m, float &gy, float &gx) {
+    Corners c;
+    corners(y, x, r, c);
+    const float2 *gp = slot_base, *gn = slot_base + g.plane;        // phase 0: pol 0, pol 1
 #pragma unroll
     for (int ky = 0; ky < 2; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 2; ++kx) {
             if (!(c.oky[ky] && c.okx[kx])) continue;
-            const float4 g = __ldg(im + ((long)c.cy[ky] * r.W + (long)c.cx[kx]));
-            const float gw = m.x * (g.x + nts * g.y) + m.y * (g.z + nts * g.w);
+            const long off = (long)c.cy[ky] * g.Wp + (long)c.cx[kx];
+            float gw = 0.0f;
+            if (m.x != 0.0f) { const float2 v = __ldg(gp + off); gw = m.x * (v.x + nts * v.y); }
+            if (m.y != 0.0f) { const float2 v = __ldg(gn + off); const float u = m.y * (v.x + nts * v.y); gw = (m.x != 0.0f) ? gw + u : u; }
             gy += gw * d1(y, c.cy[ky]) * c.wx[kx];
             gx += gw * c.wy[ky] * d1(x, c.cx[kx]);
         }
+}
+
+// dL/dmap of one bilinear flow sample: two 16-byte reductions (one per tap row)
+// into the dual-phase packed gradient map; c_k = dt * w_k, value = c_k * (g_x, g_y).
+__device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const ImgGeom &g, const Taps &tp, float dt, float gpy, float gpx) {
+    if (tp.x0 < -1) return;                                         // sample outside the map: all taps invalid
+    const int phase = tp.x0 & 1;
+    const int col = tp.x0 + phase;
+    float2 *base = gmap_phase0 + (long)phase * g.plane;
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        if (!(tp.ok[2 * ky] || tp.ok[2 * ky + 1])) continue;
+        const float cl = tp.ok[2 * ky] ? dt * tp.w[2 * ky] : 0.0f;
+        const float cr = tp.ok[2 * ky + 1] ? dt * tp.w[2 * ky + 1] : 0.0f;
+        red_add_v4(base + (long)(tp.y0 + ky) * g.Wp + col, cl * gpx, cl * gpy, cr * gpx, cr * gpy);
+    }
 }
 
 }  // namespace tef

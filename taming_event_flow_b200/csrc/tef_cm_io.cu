@@ -32,16 +32,17 @@ __global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_consta
         dst[i] = make_float2(sx[i], sy[i]);
 }
 
-// packed gradient [F][P][B][H][W] float2 -> [P][F][B][2][H][W]
+// dual-phase packed gradient [F][P][B][phase][H][Wp] float2 -> [P][F][B][2][H][W]
 __global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__restrict__ packed, float *__restrict__ out, int F, int P, int B,
-                                                               long HW) {
+                                                               int W, long HW, ImgGeom g) {
     const int fp = blockIdx.z, b = blockIdx.y;
     const int f = fp / P, t = fp % P;
-    const float2 *src = packed + (((long)f * P + t) * B + b) * HW;
+    const float2 *src = packed + (((long)f * P + t) * B + b) * 2 * g.plane;
     float *ox = out + ((((long)t * F + f) * B + b) * 2) * HW, *oy = ox + HW;
     for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < HW; i += (long)gridDim.x * kThreads) {
-        const float2 g = src[i];
-        ox[i] = g.x; oy[i] = g.y;
+        const long o = (i / W) * g.Wp + (i % W);
+        const float2 a = src[o], c = src[g.plane + o + 1];
+        ox[i] = a.x + c.x; oy[i] = a.y + c.y;
     }
 }
 
@@ -78,7 +79,8 @@ extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P,
     int bx = (int)((HW + kThreads - 1) / kThreads);
     if (bx > 148 * 4) bx = 148 * 4;
     ProfScope ps(K_UNPACK_GRAD, (cudaStream_t)stream);
-    unpack_grad_kernel<<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, HW);
+    ImgGeom g; g.Wp = (W + 3) & ~1; g.plane = (long)H * g.Wp;
+    unpack_grad_kernel<<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
     return (int)cudaGetLastError();
 }
 

@@ -8,13 +8,14 @@
 //                     chain on chip (positions at every reference time), forms
 //                     the shared border mask, and splats count + time-weighted
 //                     images straight into L2-resident slot images with native
-//                     vector reductions (REDG.E.ADD.F32x2).  No per-event
-//                     intermediate (positions, indices, weights) ever reaches HBM.
+//                     16-byte vector reductions (REDG.E.ADD.F32x4, one per image row).
+//                     Indices and weights never reach HBM.
 //   iwe_reduce/finalize   per-pixel normalisation, sum of squares, non-zero count.
 //   iwe_grad_kernel + iter_bwd_kernel   gradient images in place, then one thread
-//                     per gradient-carrying event: recompute the chain, gather the
+//                     per gradient-carrying event: read the chain positions the
+//                     forward kernel kept (88 B/event, coalesced), gather the
 //                     gradient images at the corners, walk the chain in reverse and
-//                     reduce into the packed flow-gradient maps (REDG F32x2).
+//                     reduce into the packed flow-gradient maps (REDG F32x4).
 //
 // Shared-memory tiles are deliberately NOT used: on sm_100a fp32 atomicAdd on
 // shared memory compiles to an ATOMS.CAST.SPIN compare-and-swap loop, whereas
@@ -91,15 +92,22 @@ __device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
 
 __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
-    int t, b; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m)) return;
+    int t, b, row, set; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
 
     const uint64_t alive = warp_chain(p, flow_f, b, t, e.x, e.y, e.z, pos);
 
-    float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+    // gradient-carrying rows keep their chain for the backward kernel (coalesced 8-byte stores)
+    if (set == 0 && p.posbuf) {
+        float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
+        for (int tr = 0; tr <= p.P; ++tr) pb[(long)tr * p.rows_grad] = pos[tr * kThreads + threadIdx.x];
+        p.alivebuf[(long)f * p.rows_grad + row] = alive;
+    }
+
+    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
     for (int s = 0; s < p.sc.S; ++s) {
         Win w;
         if (!window_of(p, s, t, alive, w)) continue;
@@ -111,21 +119,17 @@ __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constan
             if (!p.border && !((alive >> tr) & 1ull)) continue;
             const float nts = 1.0f - fabsf((float)tr - e.x) / fdelta;         // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
-            splat(img_fb + (long)(w.slot0 + tr) * HW, p.res, q.x, q.y, nts, m);
+            splat(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m);
         }
     }
 }
 
 // one reverse chain step: reduce dL/dmap, return dL/d(source position)
-__device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, float sy, float sx,
-                                         float dt, float gpy, float gpx, float &cy_, float &cx_) {
+__device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
+                                         float sx, float dt, float gpy, float gpx, float &cy_, float &cx_) {
     Taps tp;
     sample_flow<true>(map, r, sy, sx, &tp);
-    float2 *g = gmap + (long)tp.y0 * r.W + tp.x0;
-    const int off[4] = { 0, 1, r.W, r.W + 1 };
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (tp.ok[k]) { const float c = dt * tp.w[k]; red_add_v2(g + off[k], c * gpx, c * gpy); }
+    taps_red(gmap, g, tp, dt, gpy, gpx);
     const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
     const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
     const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
@@ -134,17 +138,19 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
     cx_ = gpx + dt * (dvy_dx * gpy + dvx_dx * gpx);
 }
 
+// One thread per gradient-carrying event.  Chain positions come from the forward kernel's posbuf
+// (coalesced loads); per node: gather the gradient images at the corners, add what flows back from the
+// next node, reduce into the packed flow-gradient map and step towards the event's own window.
 __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constant__ CmParams p) {
-    extern __shared__ float2 pos[];
-    int t, b; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m)) return;
+    int t, b, row, set; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
-    float2 *gflow_f = p.gflow + (long)f * p.P * p.B * HW;
+    float2 *gflow_f = p.gflow + (long)f * p.P * p.B * 2 * p.ig.plane;
     const float ts = e.x, y0 = e.y, x0 = e.z;
-
-    const uint64_t alive = warp_chain(p, flow_f, b, t, ts, y0, x0, pos);
+    const uint64_t alive = p.alivebuf[(long)f * p.rows_grad + row];
+    const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
 
     // windows of every scale, and the range of nodes that receive an image gradient
     Win win[TEF_MAX_SCALES];
@@ -158,46 +164,56 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
         hi_node = max(hi_node, min(win[s].high_tref - 1, t + win[s].delta));
     }
     if (!has) return;
-    const float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+    const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         for (int s = 0; s < p.sc.S; ++s) {
             if (!((has >> s) & 1u) || !feeds(win[s], tr, t)) continue;
             const float nts = 1.0f - fabsf((float)tr - ts) / (float)win[s].delta;
-            iwe_grad(img_fb + (long)(win[s].slot0 + tr) * HW, p.res, q.x, q.y, nts, m, gy, gx);
+            iwe_grad(img_fb + (long)(win[s].slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
 
     // reverse of the forward chain: nodes hi_node .. t+1 (nodes beyond carry no gradient)
     float cy_ = 0.f, cx_ = 0.f;
-    for (int tr = min(hi_node, p.P); tr >= t + 1; --tr) {
-        const bool al = ((alive >> tr) & 1ull) != 0;
-        float gy = 0.f, gx = 0.f;
-        if (al) node_grad(tr, pos[tr * kThreads + threadIdx.x], gy, gx);
-        const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
-        cy_ = 0.f; cx_ = 0.f;
-        if (gpy != 0.f || gpx != 0.f) {
+    {
+        int tr = min(hi_node, p.P);
+        float2 q = (tr >= t + 1) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        for (; tr >= t + 1; --tr) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(y0, x0) : pos[(tr - 1) * kThreads + threadIdx.x];
-            const float dt = first ? ((float)tr - ts) : 1.0f;
-            const long mo = ((long)(tr - 1) * p.B + b) * HW;
-            step_bwd(flow_f + mo, gflow_f + mo, p.res, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr - 1) * p.rows_grad];
+            const bool al = ((alive >> tr) & 1ull) != 0;
+            float gy = 0.f, gx = 0.f;
+            if (al) node_grad(tr, q, gy, gx);
+            const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+            cy_ = 0.f; cx_ = 0.f;
+            if (gpy != 0.f || gpx != 0.f) {
+                const float dt = first ? ((float)tr - ts) : 1.0f;
+                const long mo = (long)(tr - 1) * p.B + b;
+                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            }
+            q = src;
         }
     }
     // reverse of the backward chain: nodes lo_node .. t
     cy_ = 0.f; cx_ = 0.f;
-    for (int tr = max(lo_node, 0); tr <= t; ++tr) {
-        const bool al = ((alive >> tr) & 1ull) != 0;
-        float gy = 0.f, gx = 0.f;
-        if (al) node_grad(tr, pos[tr * kThreads + threadIdx.x], gy, gx);
-        const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
-        cy_ = 0.f; cx_ = 0.f;
-        if (gpy != 0.f || gpx != 0.f) {
+    {
+        int tr = max(lo_node, 0);
+        float2 q = (tr <= t) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        for (; tr <= t; ++tr) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(y0, x0) : pos[(tr + 1) * kThreads + threadIdx.x];
-            const float dt = first ? ((float)tr - ts) : -1.0f;
-            const long mo = ((long)tr * p.B + b) * HW;
-            step_bwd(flow_f + mo, gflow_f + mo, p.res, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr + 1) * p.rows_grad];
+            const bool al = ((alive >> tr) & 1ull) != 0;
+            float gy = 0.f, gx = 0.f;
+            if (al) node_grad(tr, q, gy, gx);
+            const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+            cy_ = 0.f; cx_ = 0.f;
+            if (gpy != 0.f || gpx != 0.f) {
+                const float dt = first ? ((float)tr - ts) : -1.0f;
+                const long mo = (long)tr * p.B + b;
+                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            }
+            q = src;
         }
     }
 }
@@ -227,11 +243,9 @@ static int launch_fwd(const CmParams &p, cudaStream_t st) {
 }
 static int launch_bwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(iter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads)); attr = true; }
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_BWD, st);
-        iter_bwd_kernel<<<grid, kThreads, chain_smem(p), st>>>(p);
+        iter_bwd_kernel<<<grid, kThreads, 0, st>>>(p);
     }
     return (int)cudaGetLastError();
 }
@@ -242,9 +256,8 @@ extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 0, p);
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
-    const long HW = (long)p.H * p.W;
     const long nimg = (long)p.F * p.B * p.nslots;
-    cudaMemsetAsync(p.img, 0, sizeof(float4) * nimg * HW, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * nimg * 4 * p.ig.plane, st);
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     rc = launch_fwd(p, st);
@@ -258,9 +271,9 @@ extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 0, p);                 // same segment / bin layout as the forward call
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.ev || !p.sort.mk) return TEF_EINVAL;
+    if (p.rows_grad > 0 && (!p.posbuf || !p.alivebuf)) return TEF_EINVAL;
     grad_segments_only(p);
-    const long HW = (long)p.H * p.W;
-    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * HW, st);
+    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * 2 * p.ig.plane, st);
     rc = tef_grad_images(p, st);
     if (rc) return rc;
     rc = launch_bwd(p, st);

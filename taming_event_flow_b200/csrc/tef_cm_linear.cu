@@ -22,13 +22,13 @@ __device__ __forceinline__ bool linear_ends(const CmParams &p, float lo, float h
 }
 
 __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_constant__ CmParams p) {
-    int t, b; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m)) return;
+    int t, b, row, set; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 vxy = sample_flow<false>(p.flow + (((long)f * p.P + t) * p.B + b) * HW, p.res, e.y, e.z, nullptr);
     const float2 v = make_float2(vxy.y, vxy.x);                        // (y, x), utils/iwe.py:38
-    float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
     for (int s = 0; s < p.sc.S; ++s) {
         const int L = p.sc.L[s];
         if (t >= (L << s)) continue;
@@ -38,21 +38,21 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
         const int slot = p.sc.slot_base[s] + wi * 2;
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;    // iwe_formatting(.., high_pass, scale) (:345-351)
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
-        splat(img_fb + (long)slot * HW, p.res, fw.x, fw.y, nf, m);
-        splat(img_fb + (long)(slot + 1) * HW, p.res, bw.x, bw.y, nb, m);
+        splat(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
+        splat(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
     }
 }
 
 __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_constant__ CmParams p) {
-    int t, b; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m)) return;
+    int t, b, row, set; float4 e; float2 m;
+    if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const long mo = (((long)f * p.P + t) * p.B + b) * HW;
     Taps tp;
     const float2 vxy = sample_flow<true>(p.flow + mo, p.res, e.y, e.z, &tp);
     const float2 v = make_float2(vxy.y, vxy.x);
-    const float4 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * HW;
+    const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
     float gvy = 0.f, gvx = 0.f;
     for (int s = 0; s < p.sc.S; ++s) {
         const int L = p.sc.L[s];
@@ -64,18 +64,14 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
         float gy = 0.f, gx = 0.f;
-        iwe_grad(img_fb + (long)slot * HW, p.res, fw.x, fw.y, nf, m, gy, gx);
+        iwe_grad(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m, gy, gx);
         gvy += dth * gy; gvx += dth * gx;
         gy = 0.f; gx = 0.f;
-        iwe_grad(img_fb + (long)(slot + 1) * HW, p.res, bw.x, bw.y, nb, m, gy, gx);
+        iwe_grad(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m, gy, gx);
         gvy += dtl * gy; gvx += dtl * gx;
     }
     if (gvy == 0.f && gvx == 0.f) return;
-    float2 *g = p.gflow + mo + (long)tp.y0 * p.W + tp.x0;
-    const int off[4] = { 0, 1, p.W, p.W + 1 };
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (tp.ok[k]) red_add_v2(g + off[k], tp.w[k] * gvx, tp.w[k] * gvy);
+    taps_red(p.gflow + (((long)f * p.P + t) * p.B + b) * 2 * p.ig.plane, p.ig, tp, 1.0f, gvy, gvx);
 }
 
 }  // namespace tef
@@ -92,8 +88,7 @@ extern "C" int tef_linear_forward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 1, p);
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
-    const long HW = (long)p.H * p.W;
-    cudaMemsetAsync(p.img, 0, sizeof(float4) * (long)p.F * p.B * p.nslots * HW, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * (long)p.F * p.B * p.nslots * 4 * p.ig.plane, st);
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {
@@ -112,8 +107,7 @@ extern "C" int tef_linear_backward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.ev || !p.sort.mk) return TEF_EINVAL;
     grad_segments_only(p);
-    const long HW = (long)p.H * p.W;
-    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * HW, st);
+    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * 2 * p.ig.plane, st);
     rc = tef_grad_images(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {

@@ -15,20 +15,28 @@ __device__ __forceinline__ int scale_of_slot(const ScaleTable &sc, int q) {
     return s;
 }
 
-__global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float4 *__restrict__ img, double *__restrict__ acc_sum,
-                                                              int *__restrict__ acc_nnz, long HW) {
+// sum of the two phases of one pixel: (count, time-weighted count) of one polarity
+__device__ __forceinline__ float2 pixel_sum(const float2 *__restrict__ slot_base, const ImgGeom &g, int pol, long o) {
+    const float2 a = slot_base[(long)pol * g.plane + o];                 // phase 0: column x
+    const float2 b = slot_base[(long)(2 + pol) * g.plane + o + 1];       // phase 1: column x + 1
+    return make_float2(a.x + b.x, a.y + b.y);
+}
+
+__global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__restrict__ img, double *__restrict__ acc_sum,
+                                                              int *__restrict__ acc_nnz, int W, long HW, ImgGeom g) {
     const long image = blockIdx.y;
-    const float4 *im = img + image * HW;
+    const float2 *im = img + image * 4 * g.plane;
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     double acc = 0.0;
     int cnt = 0;
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
-        const float4 v = im[i];                       // cnt+, ts+, cnt-, ts-
-        const float ap = v.y / (v.x + 1e-9f);         // loss/flow.py:727
-        const float an = v.w / (v.z + 1e-9f);
+        const long o = (i / W) * g.Wp + (i % W);
+        const float2 vp = pixel_sum(im, g, 0, o), vn = pixel_sum(im, g, 1, o);
+        const float ap = vp.y / (vp.x + 1e-9f);       // loss/flow.py:727
+        const float an = vn.y / (vn.x + 1e-9f);
         acc += (double)(ap * ap) + (double)(an * an); // :123
-        cnt += ((v.x + v.z) != 0.0f);                 // :125
+        cnt += ((vp.x + vn.x) != 0.0f);               // :125
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -80,18 +88,19 @@ __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constan
     const int s = scale_of_slot(p.sc, q);
     const float div_a = p.linear ? 2.0f : (float)(2 * p.sc.delta[s] + 1);
     const float cf = upstream(__ldg(p.grad_out), p.F, p.sc.S, div_a, s) / p.den[image];
-    float4 *im = p.img + image * HW;
+    float2 *im = p.img + image * 4 * p.ig.plane;
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
-        const float4 v = im[i];
-        const float dp = v.x + 1e-9f, dn = v.z + 1e-9f;
-        const float ap = v.y / dp, an = v.w / dn;
-        const float gap = cf * (2.0f * ap), gan = cf * (2.0f * an);
-        float4 g;
-        g.y = gap / dp; g.x = -(gap * (ap / dp));
-        g.w = gan / dn; g.z = -(gan * (an / dn));
-        im[i] = g;
+        const long o = (i / p.W) * p.ig.Wp + (i % p.W);
+#pragma unroll
+        for (int pol = 0; pol < 2; ++pol) {
+            const float2 v = pixel_sum(im, p.ig, pol, o);
+            const float d = v.x + 1e-9f;
+            const float a = v.y / d;
+            const float ga = cf * (2.0f * a);
+            im[(long)pol * p.ig.plane + o] = make_float2(-(ga * (a / d)), ga / d);    // (dL/dcount, dL/dtime-weighted), phase-0 plane
+        }
     }
 }
 
@@ -105,7 +114,7 @@ int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st) {
     cudaMemsetAsync(p.acc_sum, 0, sizeof(double) * nimg, st);
     cudaMemsetAsync(p.acc_nnz, 0, sizeof(int) * nimg, st);
     dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), nimg);
-    { ProfScope ps(K_IWE_REDUCE, st); iwe_reduce_kernel<<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, HW); }
+    { ProfScope ps(K_IWE_REDUCE, st); iwe_reduce_kernel<<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig); }
     { ProfScope ps(K_FINALIZE, st); finalize_kernel<<<1, kThreads, 0, st>>>(p); }
     return (int)cudaGetLastError();
 }
@@ -126,14 +135,21 @@ extern "C" int tef_cm_num_slots(const tef_cm_desc *d, int linear) {
     return build_scales(d, linear, sc);
 }
 
-extern "C" int tef_cm_sort_workspace(const tef_cm_desc *d, int linear, long *nbins, long *nsums, long *rows) {
+extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     CmParams p;
     int rc = fill_params(d, linear, p);
     if (rc) return rc;
+    if (!out) return TEF_EINVAL;
     long r = 0;
     for (int s = 0; s < p.seg.nseg; ++s) r += (long)p.B * p.seg.n[s];
-    if (nbins) *nbins = p.sort.nbins + 1;
-    if (nsums) *nsums = p.sort.nbins / 2048 + 2;
-    if (rows) *rows = r;
+    out[0] = p.nslots;
+    out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2;     // floats in img
+    out[2] = (long)p.F * p.P * p.B * 2 * p.ig.plane * 2;          // floats in gflow
+    out[3] = p.sort.nbins + 1;                                    // ints in sort_bins
+    out[4] = p.sort.nbins / 2048 + 2;                             // ints in sort_sums
+    out[5] = r;                                                   // rows of sorted_ev / sorted_mk
+    out[6] = p.rows_grad;                                         // gradient-carrying rows
+    out[7] = linear ? 0 : (long)p.F * (p.P + 1) * p.rows_grad * 2; // floats in posbuf (alivebuf: F * rows_grad u64)
+    out[8] = p.ig.Wp;
     return 0;
 }

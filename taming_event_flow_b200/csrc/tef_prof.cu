@@ -52,7 +52,14 @@ static void drain() {
 
 using namespace tef;
 
-extern "C" void tef_prof_enable(int on) { std::lock_guard<std::mutex> lk(g_mu); if (!on) drain(); g_on = on != 0; }
+extern "C" void tef_prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!on) drain();
+    if (on && g_free.size() < 2048) {               // create the event pool outside any timed region
+        while (g_free.size() < 2048) { Pair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.id = 0; g_free.push_back(p); }
+    }
+    g_on = on != 0;
+}
 extern "C" void tef_prof_reset(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     drain();

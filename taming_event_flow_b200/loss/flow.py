@@ -169,33 +169,36 @@ class BaseEventWarping(torch.nn.Module):
                 d.mk[k][t] = w.mk[k][t].data_ptr()
                 d.n[k][t] = w.n[k][t]
         d.flow = w.packed.data_ptr()
-        if w.sort is not None:
-            d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk = (x.data_ptr() for x in w.sort)
         return d
 
     def _forward_kernels(self, w):
         F, B, H, W = w.shape
         d = self._desc(w)
-        nslots = lib().tef_cm_num_slots(ctypes.byref(d), int(self._linear))
-        check(min(nslots, 0), "tef_cm_num_slots")
+        sz = (ctypes.c_long * 9)()
+        check(lib().tef_cm_sizes(ctypes.byref(d), int(self._linear), sz), "tef_cm_sizes")
+        nslots, n_img, _, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp = (int(v) for v in sz)
         dev = w.packed.device
-        nb, nsum, rows = ctypes.c_long(), ctypes.c_long(), ctypes.c_long()
-        check(lib().tef_cm_sort_workspace(ctypes.byref(d), int(self._linear), ctypes.byref(nb), ctypes.byref(nsum), ctypes.byref(rows)),
-              "tef_cm_sort_workspace")
-        w.sort = (torch.empty((nb.value,), dtype=torch.int32, device=dev), torch.empty((nsum.value,), dtype=torch.int32, device=dev),
-                  torch.empty((max(rows.value, 1), 4), dtype=torch.float32, device=dev),
-                  torch.empty((max(rows.value, 1), 2), dtype=torch.float32, device=dev))
-        d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk = (x.data_ptr() for x in w.sort)
-        w.img = torch.empty((F, B, nslots, H, W, 4), dtype=torch.float32, device=dev)
+        i32, f32 = torch.int32, torch.float32
+        w.sort = (torch.empty((n_bins,), dtype=i32, device=dev), torch.empty((n_sums,), dtype=i32, device=dev),
+                  torch.empty((max(rows, 1), 4), dtype=f32, device=dev), torch.empty((max(rows, 1), 2), dtype=f32, device=dev),
+                  torch.empty((max(n_pos, 1),), dtype=f32, device=dev), torch.empty((max(F * rows_grad, 1),), dtype=torch.int64, device=dev))
+        w.img = torch.empty((n_img,), dtype=f32, device=dev)
         w.acc_sum = torch.empty((F, B, nslots), dtype=torch.float64, device=dev)
-        w.acc_nnz = torch.empty((F, B, nslots), dtype=torch.int32, device=dev)
-        w.den = torch.empty((F, B, nslots), dtype=torch.float32, device=dev)
-        loss = torch.empty((1,), dtype=torch.float32, device=dev)
-        d.img, d.acc_sum, d.acc_nnz, d.den, d.loss = (x.data_ptr() for x in (w.img, w.acc_sum, w.acc_nnz, w.den, loss))
+        w.acc_nnz = torch.empty((F, B, nslots), dtype=i32, device=dev)
+        w.den = torch.empty((F, B, nslots), dtype=f32, device=dev)
+        w.nslots = nslots
+        loss = torch.empty((1,), dtype=f32, device=dev)
+        self._fill_workspace(d, w)
+        d.acc_sum, d.acc_nnz, d.loss = w.acc_sum.data_ptr(), w.acc_nnz.data_ptr(), loss.data_ptr()
         fn = lib().tef_linear_forward if self._linear else lib().tef_iterative_forward
         check(fn(ctypes.byref(d), stream()), "tef_linear_forward" if self._linear else "tef_iterative_forward")
         w.consumed = False
         return loss.view(())
+
+    @staticmethod
+    def _fill_workspace(d, w):
+        d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk, d.posbuf, d.alivebuf = (x.data_ptr() for x in w.sort)
+        d.img, d.den = w.img.data_ptr(), w.den.data_ptr()
 
     def _backward_kernels(self, w, gout):
         if w.consumed:
@@ -204,15 +207,27 @@ class BaseEventWarping(torch.nn.Module):
         P = self._max_passes()
         d = self._desc(w)
         dev = w.packed.device
-        gpacked = torch.empty((F, P, B, H, W, 2), dtype=torch.float32, device=dev)
+        gpacked = torch.empty((F, P, B, 2, H, w.Wp, 2), dtype=torch.float32, device=dev)
         grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)
         g = gout.detach().float().contiguous().reshape(1)
-        d.img, d.den, d.gflow, d.grad_out = w.img.data_ptr(), w.den.data_ptr(), gpacked.data_ptr(), g.data_ptr()
+        self._fill_workspace(d, w)
+        d.gflow, d.grad_out = gpacked.data_ptr(), g.data_ptr()
         fn = lib().tef_linear_backward if self._linear else lib().tef_iterative_backward
         check(fn(ctypes.byref(d), stream()), "tef_linear_backward" if self._linear else "tef_iterative_backward")
         check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, stream()), "tef_unpack_flow_grad")
         w.consumed = True
         return grads
+
+    def images(self):
+        """Diagnostic view of the accumulated images of the last forward call (before backward):
+        [F, B, slots, 4, H, W] with channels (count+, count-, time-weighted+, time-weighted-)."""
+        w = self._win
+        if w.img is None or w.consumed:
+            raise RuntimeError("images() is only available between forward() and backward()")
+        F, B, H, W = w.shape
+        v = w.img.view(F, B, w.nslots, 2, 2, H, w.Wp, 2)              # [.., phase, pol, H, Wp, (count, tw)]
+        s = v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]
+        return torch.stack([s[:, :, :, 0, :, :, 0], s[:, :, :, 1, :, :, 0], s[:, :, :, 0, :, :, 1], s[:, :, :, 1, :, :, 1]], dim=3)
 
     # ---------------------------------------------------------------- forward
     def _cm_loss(self):

@@ -34,8 +34,7 @@ def _run_gpu(kind, cfg, flows, events, masks, d_events, d_masks, border=True, lo
         m.update(fl[t], torch.as_tensor(events[t]).to(dev).clone(), torch.as_tensor(masks[t]).to(dev).clone(),
                  torch.as_tensor(d_events[t]).to(dev).clone(), torch.as_tensor(d_masks[t]).to(dev).clone())
     loss = m()
-    img = m._win.img.detach().cpu().numpy().copy()          # [F,B,slots,H,W,(cnt+,ts+,cnt-,ts-)]
-    iwe = np.stack([img[..., 0], img[..., 2], img[..., 1], img[..., 3]], axis=3)   # -> [F,B,slots,4,H,W] oracle order
+    iwe = m.images().cpu().numpy()                           # [F,B,slots,4,H,W] in the oracle's channel order
     out = {"loss": float(loss.item()), "iwe": iwe, "module": m}
     if backward:
         loss.backward()
