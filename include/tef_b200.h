@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TEF_MAX_PASSES 40   /* passes_loss (after the mode-"four" doubling)          */
+#define TEF_MAX_PASSES 31   /* passes_loss (after the mode-"four" doubling); in-image bits fit 32 bits */
 #define TEF_MAX_SCALES 6    /* scales_loss                                            */
 #define TEF_MAX_FLOWS 8     /* flow maps per pass (RecEVFlowNet emits 4)              */
 
@@ -68,7 +68,7 @@ typedef struct tef_cm_desc {
     void *sorted_ev;       /* float4 [rows]: (ts, y, x, sample index bits), tile-sorted */
     void *sorted_mk;       /* float2 [rows]                                            */
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
-    void *alivebuf;        /* uint64 [F][rows_grad] cumulative in-image bits           */
+    void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
 } tef_cm_desc;
 
 /* buffer sizes for the events currently described by `d`; out[9] =

@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libtef_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-MAX_PASSES = 40
+MAX_PASSES = 31
 MAX_SCALES = 6
 MAX_FLOWS = 8
 

@@ -57,7 +57,7 @@ struct CmParams {
     float2 *gflow;
     float2 *img;
     float2 *posbuf;          // [(P+1)][rows_grad] chain positions of the gradient-carrying rows (Iterative)
-    unsigned long long *alivebuf;   // [rows_grad]
+    uint32_t *alivebuf;      // [F][rows_grad] cumulative in-image bits (bit tref)
     long rows_grad;
     double *acc_sum;
     int *acc_nnz;
@@ -110,7 +110,7 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     p.res = Res::make(d->H, d->W);
     p.flow = (const float2 *)d->flow; p.gflow = (float2 *)d->gflow; p.img = (float2 *)d->img;
     p.ig.Wp = (d->W + 3) & ~1; p.ig.plane = (long)d->H * p.ig.Wp;
-    p.posbuf = (float2 *)d->posbuf; p.alivebuf = (unsigned long long *)d->alivebuf;
+    p.posbuf = (float2 *)d->posbuf; p.alivebuf = (uint32_t *)d->alivebuf;
     p.acc_sum = d->acc_sum; p.acc_nnz = d->acc_nnz; p.den = d->den; p.loss = d->loss; p.grad_out = d->grad_out;
     p.nslots = build_scales(d, linear, p.sc);
     int ns = 0, blk = 0;

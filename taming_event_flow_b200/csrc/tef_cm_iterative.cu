@@ -32,36 +32,42 @@ namespace tef {
 // loops rolled and the register count low for any P; they never travel to HBM.
 // The pass index t is uniform per CTA, so the loop bounds do not diverge.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_f, int b, int t,
-                                               float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */) {
-    const long HW = (long)p.H * p.W;
-    uint64_t alive = 0;
+__device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
+                                               int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */) {
+    const long stride = (long)p.B * p.H * p.W;     // one pass further
+    uint32_t alive = 0;
+    // the event's own location may lie outside the sensor (generic sample); every later position is inside
+    const bool in0 = inside(y0, x0, p.res);
     float y = y0, x = x0, tprev = ts;
-    bool al = true;
-    for (int tr = t + 1; tr <= p.P; ++tr) {        // forward: sample map tr-1, land on node tr
+    bool al = true, safe = in0;
+    const float2 *map = flow_fb + (long)t * stride;
+    float2 *pw = pos + (t + 1) * kThreads + threadIdx.x;
+    for (int tr = t + 1; tr <= p.P; ++tr, map += stride, pw += kThreads) {   // forward: sample map tr-1, land on node tr
         if (al) {
-            const float2 *map = flow_f + ((long)(tr - 1) * p.B + b) * HW;
-            float2 v = sample_flow<false>(map, p.res, y, x, nullptr);
-            float dt = (float)tr - tprev;          // utils/iwe.py:14
+            const float2 v = safe ? sample_flow_inside<false>(map, p.res, y, x, nullptr) : sample_flow<false>(map, p.res, y, x, nullptr);
+            const float dt = (float)tr - tprev;    // utils/iwe.py:14
             y = y + dt * v.y; x = x + dt * v.x;
             al = inside(y, x, p.res);              // utils/iwe.py:52-59
-            if (al) alive |= (1ull << tr);
+            if (al) alive |= (1u << tr);
+            safe = true;
         }
         tprev = (float)tr;
-        pos[tr * kThreads + threadIdx.x] = make_float2(y, x);
+        *pw = make_float2(y, x);
     }
-    y = y0; x = x0; tprev = ts; al = true;
-    for (int tr = t; tr >= 0; --tr) {              // backward: sample map tr, land on node tr
+    y = y0; x = x0; tprev = ts; al = true; safe = in0;
+    map = flow_fb + (long)t * stride;
+    pw = pos + t * kThreads + threadIdx.x;
+    for (int tr = t; tr >= 0; --tr, map -= stride, pw -= kThreads) {         // backward: sample map tr, land on node tr
         if (al) {
-            const float2 *map = flow_f + ((long)tr * p.B + b) * HW;
-            float2 v = sample_flow<false>(map, p.res, y, x, nullptr);
-            float dt = (float)tr - tprev;
+            const float2 v = safe ? sample_flow_inside<false>(map, p.res, y, x, nullptr) : sample_flow<false>(map, p.res, y, x, nullptr);
+            const float dt = (float)tr - tprev;
             y = y + dt * v.y; x = x + dt * v.x;
             al = inside(y, x, p.res);
-            if (al) alive |= (1ull << tr);
+            if (al) alive |= (1u << tr);
+            safe = true;
         }
         tprev = (float)tr;
-        pos[tr * kThreads + threadIdx.x] = make_float2(y, x);
+        *pw = make_float2(y, x);
     }
     return alive;
 }
@@ -71,7 +77,7 @@ struct Win {
     int lo, hi, low_tref, high_tref, delta, slot0;
     bool shared_ok;
 };
-__device__ __forceinline__ bool window_of(const CmParams &p, int s, int t, uint64_t alive, Win &w) {
+__device__ __forceinline__ bool window_of(const CmParams &p, int s, int t, uint32_t alive, Win &w) {
     const int L = p.sc.L[s];
     if (t >= (L << s)) return false;               // passes beyond 2^s windows are unused at this scale
     const int wi = t / L;
@@ -79,7 +85,7 @@ __device__ __forceinline__ bool window_of(const CmParams &p, int s, int t, uint6
     w.lo = wi * L; w.hi = w.lo + L;
     w.low_tref = w.lo; w.high_tref = w.hi + 1;
     if (p.mode == 4) { w.low_tref = w.lo + w.delta; w.high_tref = w.lo + 3 * w.delta + 1; }
-    const uint64_t m = ((1ull << w.high_tref) - 1ull) & ~((1ull << w.low_tref) - 1ull);
+    const uint32_t m = (uint32_t)((1ull << w.high_tref) - 1ull) & ~((1u << w.low_tref) - 1u);
     w.shared_ok = (alive & m) == m;                // product of the masks over all tref (:671-681)
     w.slot0 = p.sc.slot_base[s] + wi * p.sc.ntau[s] - w.low_tref;
     return true;
@@ -96,9 +102,7 @@ __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constan
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
-    const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
-
-    const uint64_t alive = warp_chain(p, flow_f, b, t, e.x, e.y, e.z, pos);
+    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * HW, t, e.x, e.y, e.z, pos);
 
     // gradient-carrying rows keep their chain for the backward kernel (coalesced 8-byte stores)
     if (set == 0 && p.posbuf) {
@@ -112,12 +116,12 @@ __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constan
         Win w;
         if (!window_of(p, s, t, alive, w)) continue;
         if (p.border && !w.shared_ok) continue;
-        const float fdelta = (float)w.delta;
+        const float fdelta = (float)w.delta, rdelta = 1.0f / fdelta;
         // reference times fed by window t: max(lo, tr-delta) <= t < min(hi, tr+delta)  (:685-686)
         const int tr0 = max(w.low_tref, t - w.delta + 1), tr1 = min(w.high_tref - 1, t + w.delta);
         for (int tr = tr0; tr <= tr1; ++tr) {
-            if (!p.border && !((alive >> tr) & 1ull)) continue;
-            const float nts = 1.0f - fabsf((float)tr - e.x) / fdelta;         // loss/flow.py:94-95
+            if (!p.border && !((alive >> tr) & 1u)) continue;
+            const float nts = 1.0f - div_const(fabsf((float)tr - e.x), fdelta, rdelta);   // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
             splat(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m);
         }
@@ -128,7 +132,8 @@ __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constan
 __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
                                          float sx, float dt, float gpy, float gpx, float &cy_, float &cx_) {
     Taps tp;
-    sample_flow<true>(map, r, sy, sx, &tp);
+    if (inside(sy, sx, r)) sample_flow_inside<true>(map, r, sy, sx, &tp);
+    else sample_flow<true>(map, r, sy, sx, &tp);
     taps_red(gmap, g, tp, dt, gpy, gpx);
     const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
     const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
     float2 *gflow_f = p.gflow + (long)f * p.P * p.B * 2 * p.ig.plane;
     const float ts = e.x, y0 = e.y, x0 = e.z;
-    const uint64_t alive = p.alivebuf[(long)f * p.rows_grad + row];
+    const uint32_t alive = p.alivebuf[(long)f * p.rows_grad + row];
     const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
 
     // windows of every scale, and the range of nodes that receive an image gradient
@@ -169,7 +174,8 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         for (int s = 0; s < p.sc.S; ++s) {
             if (!((has >> s) & 1u) || !feeds(win[s], tr, t)) continue;
-            const float nts = 1.0f - fabsf((float)tr - ts) / (float)win[s].delta;
+            const float fdelta = (float)win[s].delta;
+            const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
             iwe_grad(img_fb + (long)(win[s].slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
         for (; tr >= t + 1; --tr) {
             const bool first = (tr - 1 == t);
             const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr - 1) * p.rows_grad];
-            const bool al = ((alive >> tr) & 1ull) != 0;
+            const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
             const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
         for (; tr <= t; ++tr) {
             const bool first = (tr == t);
             const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr + 1) * p.rows_grad];
-            const bool al = ((alive >> tr) & 1ull) != 0;
+            const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
             const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;

@@ -17,15 +17,29 @@ struct Res {
     int H, W;
     float hm1, wm1;   // (float)(H-1), (float)(W-1)
     float sh, sw;     // (H-1)/2, (W-1)/2  (ATen's align_corners=True scaling factor)
+    float rhm1, rwm1; // RN(1/hm1), RN(1/wm1) for div_const()
     __host__ __device__ static Res make(int H, int W) {
         Res r; r.H = H; r.W = W; r.hm1 = (float)(H - 1); r.wm1 = (float)(W - 1);
-        r.sh = r.hm1 / 2.0f; r.sw = r.wm1 / 2.0f; return r;
+        r.sh = r.hm1 / 2.0f; r.sw = r.wm1 / 2.0f; r.rhm1 = 1.0f / r.hm1; r.rwm1 = 1.0f / r.wm1; return r;
     }
 };
 
-// purge_unfeasible (utils/iwe.py:52-57): inclusive bounds [0, res-1]
+// IEEE-correct a / c for a divisor known in advance, rc = RN(1/c): one Newton correction of the product
+// (Markstein).  Three instructions instead of the generic division's rcp + refinement + range check.
+// Verified exhaustively against a / c (every fp32 a in [0, 2c+4], c in {127, 479, 639, 255, 259, 345, 1023, 1279, 1..40, ...});
+// it only deviates when the quotient is denormal, hence the guard.
+__device__ __forceinline__ float div_const(float a, float c, float rc) {
+    if (fabsf(a) >= 1e-30f) {
+        const float q0 = a * rc;
+        const float r0 = __fmaf_rn(-q0, c, a);
+        return __fmaf_rn(r0, rc, q0);
+    }
+    return a / c;
+}
+
+// purge_unfeasible (utils/iwe.py:52-57): inclusive bounds [0, res-1]; (float)H - 1.0f == (float)(H-1) for any image size
 __device__ __forceinline__ bool inside(float y, float x, const Res &r) {
-    return (y >= 0.0f) && (y <= (float)r.H - 1.0f) && (x >= 0.0f) && (x <= (float)r.W - 1.0f);
+    return (y >= 0.0f) && (y <= r.hm1) && (x >= 0.0f) && (x <= r.wm1);
 }
 
 // bilinear sampling set-up = utils/iwe.py:17-40 (normalisation) + ATen grid_sampler_2d
@@ -37,8 +51,8 @@ struct Bil {
     bool ok[4];
 };
 __device__ __forceinline__ void bilinear_setup(const Res &r, float y, float x, Bil &b) {
-    float gy = (2.0f * y) / r.hm1 - 1.0f;          // utils/iwe.py:30
-    float gx = (2.0f * x) / r.wm1 - 1.0f;          // utils/iwe.py:31
+    float gy = div_const(2.0f * y, r.hm1, r.rhm1) - 1.0f;      // utils/iwe.py:30
+    float gx = div_const(2.0f * x, r.wm1, r.rwm1) - 1.0f;      // utils/iwe.py:31
     float iy = (gy + 1.0f) * r.sh;                 // ATen unnormalize, align_corners=True
     float ix = (gx + 1.0f) * r.sw;
     float fy0 = floorf(iy), fx0 = floorf(ix);
@@ -82,6 +96,39 @@ __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, co
         tp->ax = b.ax; tp->ay = b.ay; tp->y0 = b.y0; tp->x0 = b.x0;
     }
     return make_float2(ox, oy);   // (.x = x-flow, .y = y-flow)
+}
+
+// Same sample for a position known to satisfy inside(): then 0 <= iy <= H-1 and 0 <= ix <= W-1 exactly
+// (gy + 1 is in [0, 2]), the north-west tap always exists and only the +1 taps need a bounds test.
+// Bit-identical to sample_flow() on such positions.
+template <bool KEEP>
+__device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
+    const float gy = div_const(2.0f * y, r.hm1, r.rhm1) - 1.0f;
+    const float gx = div_const(2.0f * x, r.wm1, r.rwm1) - 1.0f;
+    const float iy = (gy + 1.0f) * r.sh, ix = (gx + 1.0f) * r.sw;
+    const float fy0 = floorf(iy), fx0 = floorf(ix);
+    const float w_ = ix - fx0, e_ = 1.0f - w_;
+    const float n_ = iy - fy0, s_ = 1.0f - n_;
+    const int y0 = (int)fy0, x0 = (int)fx0;
+    const bool oy1 = y0 + 1 < r.H, ox1 = x0 + 1 < r.W;
+    const float2 *p = map + (y0 * r.W + x0);
+    const float2 z = make_float2(0.f, 0.f);
+    const float2 v0 = __ldg(p);
+    const float2 v1 = ox1 ? __ldg(p + 1) : z;
+    const float2 v2 = oy1 ? __ldg(p + r.W) : z;
+    const float2 v3 = (oy1 && ox1) ? __ldg(p + r.W + 1) : z;
+    const float w0 = s_ * e_, w1 = s_ * w_, w2 = n_ * e_, w3 = n_ * w_;
+    float ox = v0.x * w0, oy = v0.y * w0;
+    ox = __fmaf_rn(v1.x, w1, ox); oy = __fmaf_rn(v1.y, w1, oy);
+    ox = __fmaf_rn(v2.x, w2, ox); oy = __fmaf_rn(v2.y, w2, oy);
+    ox = __fmaf_rn(v3.x, w3, ox); oy = __fmaf_rn(v3.y, w3, oy);
+    if (KEEP) {
+        tp->w[0] = w0; tp->w[1] = w1; tp->w[2] = w2; tp->w[3] = w3;
+        tp->v[0] = v0; tp->v[1] = v1; tp->v[2] = v2; tp->v[3] = v3;
+        tp->ok[0] = true; tp->ok[1] = ox1; tp->ok[2] = oy1; tp->ok[3] = oy1 && ox1;
+        tp->ax = w_; tp->ay = n_; tp->y0 = y0; tp->x0 = x0;
+    }
+    return make_float2(ox, oy);
 }
 
 // get_interpolation, bilinear branch (utils/iwe.py:85-107), one event

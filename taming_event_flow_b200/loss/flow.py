@@ -181,7 +181,7 @@ class BaseEventWarping(torch.nn.Module):
         i32, f32 = torch.int32, torch.float32
         w.sort = (torch.empty((n_bins,), dtype=i32, device=dev), torch.empty((n_sums,), dtype=i32, device=dev),
                   torch.empty((max(rows, 1), 4), dtype=f32, device=dev), torch.empty((max(rows, 1), 2), dtype=f32, device=dev),
-                  torch.empty((max(n_pos, 1),), dtype=f32, device=dev), torch.empty((max(F * rows_grad, 1),), dtype=torch.int64, device=dev))
+                  torch.empty((max(n_pos, 1),), dtype=f32, device=dev), torch.empty((max(F * rows_grad, 1),), dtype=i32, device=dev))
         w.img = torch.empty((n_img,), dtype=f32, device=dev)
         w.acc_sum = torch.empty((F, B, nslots), dtype=torch.float64, device=dev)
         w.acc_nnz = torch.empty((F, B, nslots), dtype=i32, device=dev)
