@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libtef_b200.so")
+LIB_PATH = os.environ.get("TEF_B200_LIB", os.path.join(_HERE, "libtef_b200.so"))   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_PASSES = 31
@@ -72,7 +72,8 @@ def build(force=False, verbose=False):
     if not (force or needs_build()):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + sources()
+    extra = os.environ.get("TEF_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise TefError("nvcc failed:\n" + r.stdout + r.stderr)

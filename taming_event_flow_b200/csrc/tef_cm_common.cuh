@@ -192,11 +192,12 @@ __device__ __forceinline__ float2 *img_plane(float2 *slot_base, const ImgGeom &g
 // (w_left, w_left*n, w_right, w_right*n) into the plane of the event's polarity.
 // Corner coordinates, weights and in-image tests are exactly get_interpolation's (utils/iwe.py:85-107);
 // a corner outside the image (or with weight 0) contributes an exact +0.
+template <bool INSIDE>
 __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts, float2 m) {
     Corners c;
-    corners(y, x, r, c);
-    if (!(c.okx[0] || c.okx[1])) return;
-    const int xl = c.okx[0] ? (int)c.cx[0] : (int)c.cx[1] - 1;      // column of the left corner (-1 .. W-1)
+    corners<INSIDE>(y, x, r, c);
+    if (!INSIDE && !(c.okx[0] || c.okx[1])) return;
+    const int xl = (INSIDE || c.okx[0]) ? (int)c.cx[0] : (int)c.cx[1] - 1;      // column of the left corner (-1 .. W-1)
     const int phase = xl & 1;
     const int col = xl + phase;                                     // even -> 16-byte aligned pair
     const int pol = (m.x != 0.0f) ? 0 : 1;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
         const float wl = c.okx[0] ? c.wy[ky] * c.wx[0] : 0.0f;
         const float wr = c.okx[1] ? c.wy[ky] * c.wx[1] : 0.0f;
         if (wl == 0.0f && wr == 0.0f) continue;
-        const long off = (long)c.cy[ky] * g.Wp + col;
+        const int off = (int)c.cy[ky] * g.Wp + col;
         const float tl = wl * nts, tr = wr * nts;
         red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
         if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
@@ -217,22 +218,27 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
 
 // gradient of the loss w.r.t. the position at one reference time, through the bilinear splat weights
 // (SURVEY.md Appendix A.4); the gradient images (dL/dcount, dL/dtime-weighted) live in the phase-0 planes.
+template <bool INSIDE>
 __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts,
                                          float2 m, float &gy, float &gx) {
     Corners c;
-    corners(y, x, r, c);
-    const float2 *gp = slot_base, *gn = slot_base + g.plane;        // phase 0: pol 0, pol 1
+    corners<INSIDE>(y, x, r, c);
+    const float dy[2] = { d1(y, c.cy[0]), d1(y, c.cy[1]) };
+    const float dx[2] = { d1(x, c.cx[0]), d1(x, c.cx[1]) };
+    const bool binary = (m.y == 0.0f) || (m.x == 0.0f);            // {0,1} masks: one polarity plane is read
+    const float2 *g0 = slot_base + ((m.x != 0.0f) ? 0 : g.plane);   // phase 0, plane of the (first) active polarity
+    const float m0 = (m.x != 0.0f) ? m.x : m.y;
 #pragma unroll
     for (int ky = 0; ky < 2; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 2; ++kx) {
             if (!(c.oky[ky] && c.okx[kx])) continue;
-            const long off = (long)c.cy[ky] * g.Wp + (long)c.cx[kx];
-            float gw = 0.0f;
-            if (m.x != 0.0f) { const float2 v = __ldg(gp + off); gw = m.x * (v.x + nts * v.y); }
-            if (m.y != 0.0f) { const float2 v = __ldg(gn + off); const float u = m.y * (v.x + nts * v.y); gw = (m.x != 0.0f) ? gw + u : u; }
-            gy += gw * d1(y, c.cy[ky]) * c.wx[kx];
-            gx += gw * c.wy[ky] * d1(x, c.cx[kx]);
+            const int off = (int)c.cy[ky] * g.Wp + (int)c.cx[kx];
+            const float2 v = __ldg(g0 + off);
+            float gw = m0 * (v.x + nts * v.y);
+            if (!binary) { const float2 u = __ldg(slot_base + g.plane + off); gw = gw + m.y * (u.x + nts * u.y); }
+            gy += gw * dy[ky] * c.wx[kx];
+            gx += gw * c.wy[ky] * dx[kx];
         }
 }
 

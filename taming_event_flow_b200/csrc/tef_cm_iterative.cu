@@ -24,6 +24,13 @@
 #include "tef_cm_common.cuh"
 #include "tef_prof.cuh"
 
+#ifndef TEF_FWD_MIN_BLOCKS
+#define TEF_FWD_MIN_BLOCKS 6
+#endif
+#ifndef TEF_BWD_MIN_BLOCKS
+#define TEF_BWD_MIN_BLOCKS 5
+#endif
+
 namespace tef {
 
 // ---------------------------------------------------------------------------------
@@ -96,7 +103,7 @@ __device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
     return t >= lo_e && t < hi_e;
 }
 
-__global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constant__ CmParams p) {
+__global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) iter_fwd_kernel(const __grid_constan
             if (!p.border && !((alive >> tr) & 1u)) continue;
             const float nts = 1.0f - div_const(fabsf((float)tr - e.x), fdelta, rdelta);   // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
-            splat(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m);
+            splat<true>(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m);
         }
     }
 }
@@ -146,7 +153,7 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
 // One thread per gradient-carrying event.  Chain positions come from the forward kernel's posbuf
 // (coalesced loads); per node: gather the gradient images at the corners, add what flows back from the
 // next node, reduce into the packed flow-gradient map and step towards the event's own window.
-__global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constant__ CmParams p) {
+__global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
@@ -157,26 +164,29 @@ __global__ void __launch_bounds__(kThreads) iter_bwd_kernel(const __grid_constan
     const uint32_t alive = p.alivebuf[(long)f * p.rows_grad + row];
     const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
 
-    // windows of every scale, and the range of nodes that receive an image gradient
-    Win win[TEF_MAX_SCALES];
+    // scales whose sub-window takes this event, and the range of nodes that receive an image gradient
     int lo_node = p.P + 1, hi_node = -1;
     uint32_t has = 0;
     for (int s = 0; s < p.sc.S; ++s) {
-        if (!window_of(p, s, t, alive, win[s])) continue;
-        if (p.border && !win[s].shared_ok) continue;
+        Win w;
+        if (!window_of(p, s, t, alive, w)) continue;
+        if (p.border && !w.shared_ok) continue;
         has |= 1u << s;
-        lo_node = min(lo_node, max(win[s].low_tref, t - win[s].delta + 1));
-        hi_node = max(hi_node, min(win[s].high_tref - 1, t + win[s].delta));
+        lo_node = min(lo_node, max(w.low_tref, t - w.delta + 1));
+        hi_node = max(hi_node, min(w.high_tref - 1, t + w.delta));
     }
     if (!has) return;
     const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         for (int s = 0; s < p.sc.S; ++s) {
-            if (!((has >> s) & 1u) || !feeds(win[s], tr, t)) continue;
-            const float fdelta = (float)win[s].delta;
+            if (!((has >> s) & 1u)) continue;
+            Win w;
+            window_of(p, s, t, alive, w);
+            if (!feeds(w, tr, t)) continue;
+            const float fdelta = (float)w.delta;
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
-            iwe_grad(img_fb + (long)(win[s].slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+            iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
 

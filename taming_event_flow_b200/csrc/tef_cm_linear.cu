@@ -38,8 +38,13 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
         const int slot = p.sc.slot_base[s] + wi * 2;
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;    // iwe_formatting(.., high_pass, scale) (:345-351)
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
-        splat(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
-        splat(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
+        if (p.border) {      // both ends passed purge_unfeasible: in-image fast path
+            splat<true>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
+            splat<true>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
+        } else {
+            splat<false>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
+            splat<false>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
+        }
     }
 }
 
@@ -64,10 +69,10 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
         float gy = 0.f, gx = 0.f;
-        iwe_grad(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m, gy, gx);
+        iwe_grad<false>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m, gy, gx);
         gvy += dth * gy; gvx += dth * gx;
         gy = 0.f; gx = 0.f;
-        iwe_grad(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m, gy, gx);
+        iwe_grad<false>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m, gy, gx);
         gvy += dtl * gy; gvx += dtl * gx;
     }
     if (gvy == 0.f && gvx == 0.f) return;

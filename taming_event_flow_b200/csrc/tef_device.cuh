@@ -137,6 +137,9 @@ struct Corners {
     float wy[2], wx[2];   // clamped 1-D weights
     bool oky[2], okx[2];  // strict in-image tests (utils/iwe.py:103)
 };
+// INSIDE: the position satisfies inside(), so the top/left corners are in the image and only the
+// bottom/right ones (floor(v + 1) <= size) need the strict test.
+template <bool INSIDE = false>
 __device__ __forceinline__ void corners(float y, float x, const Res &r, Corners &c) {
     c.cy[0] = floorf(y); c.cy[1] = floorf(y + 1.0f);
     c.cx[0] = floorf(x); c.cx[1] = floorf(x + 1.0f);
@@ -144,8 +147,13 @@ __device__ __forceinline__ void corners(float y, float x, const Res &r, Corners 
     for (int k = 0; k < 2; ++k) {
         c.wy[k] = fmaxf(0.0f, 1.0f - fabsf(y - c.cy[k]));
         c.wx[k] = fmaxf(0.0f, 1.0f - fabsf(x - c.cx[k]));
-        c.oky[k] = (c.cy[k] >= 0.0f) && (c.cy[k] < (float)r.H);
-        c.okx[k] = (c.cx[k] >= 0.0f) && (c.cx[k] < (float)r.W);
+        if (INSIDE) {
+            c.oky[k] = (k == 0) || (c.cy[k] <= r.hm1);
+            c.okx[k] = (k == 0) || (c.cx[k] <= r.wm1);
+        } else {
+            c.oky[k] = (c.cy[k] >= 0.0f) && (c.cy[k] < (float)r.H);
+            c.okx[k] = (c.cx[k] >= 0.0f) && (c.cx[k] < (float)r.W);
+        }
     }
 }
 
