@@ -21,6 +21,7 @@ struct SegTable {
 
 // geometry and buffers of the tile sort (tef_cm_sort.cu)
 struct SortGeom {
+    int blk_off[kMaxSeg + 1];        // CTA ranges of the sort kernels (4 rows per thread)
     int B, H, W, tiles_x, tiles;     // 16x8-pixel tiles per sample
     long nbins;                      // nseg * B * tiles * 128
     int *bins;                       // [nbins + 1] histogram -> offsets -> bin ends
@@ -132,6 +133,8 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     g.B = d->B; g.H = d->H; g.W = d->W;
     g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
     for (int s = 0; s <= ns; ++s) p.seg.first_bin[s] = s * d->B * g.tiles * 128;
+    g.blk_off[0] = 0;
+    for (int s = 0; s < ns; ++s) g.blk_off[s + 1] = g.blk_off[s] + (int)(((long)d->B * p.seg.n[s] + kThreads * 4 - 1) / (kThreads * 4));
     g.nbins = (long)ns * d->B * g.tiles * 128;
     g.bins = (int *)d->sort_bins; g.sums = (int *)d->sort_sums;
     g.ev = (float4 *)d->sorted_ev; g.mk = (float2 *)d->sorted_mk;

@@ -25,10 +25,10 @@
 #include "tef_prof.cuh"
 
 #ifndef TEF_FWD_MIN_BLOCKS
-#define TEF_FWD_MIN_BLOCKS 6
+#define TEF_FWD_MIN_BLOCKS 5
 #endif
 #ifndef TEF_BWD_MIN_BLOCKS
-#define TEF_BWD_MIN_BLOCKS 5
+#define TEF_BWD_MIN_BLOCKS 4
 #endif
 
 namespace tef {

@@ -22,34 +22,61 @@ __device__ __forceinline__ int bin_of(const SortGeom &g, int seg, int b, float y
     return ((seg * g.B + b) * g.tiles + tile) * 128 + ((iy & 7) << 4) + (ix & 15);
 }
 
-__global__ void __launch_bounds__(kThreads) sort_hist_kernel(const __grid_constant__ CmParams p) {
-    int sg = 0;
+// Both kernels walk a segment with kSortIlp rows per thread (strided by the CTA size, so every access stays
+// coalesced): the returning atomic of the scatter has ~1 us latency and one row per thread leaves the
+// kernel latency-bound (profiles/r1_c: 11 % issue, long-scoreboard 103).
+constexpr int kSortIlp = 4;
+
+__device__ __forceinline__ bool sort_rows(const CmParams &p, int &sg, int &n, long (&row)[kSortIlp], long &nrows) {
+    sg = 0;
     const int blk = blockIdx.x;
-    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
-    const int n = p.seg.n[sg];
-    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
-    if (row >= (long)p.B * n) return;
-    const float2 m = __ldg(p.seg.mk[sg] + row);
-    if (m.x == 0.0f && m.y == 0.0f) return;        // padding rows are dropped
-    const float4 e = __ldg(p.seg.ev[sg] + row);
-    atomicAdd(p.sort.bins + bin_of(p.sort, sg, (int)(row / n), e.y, e.z), 1);
+    while (blk >= p.sort.blk_off[sg + 1]) ++sg;
+    n = p.seg.n[sg];
+    nrows = (long)p.B * n;
+    const long base = (long)(blk - p.sort.blk_off[sg]) * (kThreads * kSortIlp) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k) row[k] = base + (long)k * kThreads;
+    return base < nrows;
+}
+
+__global__ void __launch_bounds__(kThreads) sort_hist_kernel(const __grid_constant__ CmParams p) {
+    int sg, n; long row[kSortIlp], nrows;
+    if (!sort_rows(p, sg, n, row, nrows)) return;
+    float2 m[kSortIlp]; float4 e[kSortIlp];
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k) {
+        const bool ok = row[k] < nrows;
+        m[k] = ok ? __ldg(p.seg.mk[sg] + row[k]) : make_float2(0.f, 0.f);
+        e[k] = ok ? __ldg(p.seg.ev[sg] + row[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k) {
+        if (m[k].x == 0.0f && m[k].y == 0.0f) continue;            // padding rows are dropped
+        atomicAdd(p.sort.bins + bin_of(p.sort, sg, (int)(row[k] / n), e[k].y, e[k].z), 1);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const __grid_constant__ CmParams p) {
-    int sg = 0;
-    const int blk = blockIdx.x;
-    while (blk >= p.seg.blk_off[sg + 1]) ++sg;
-    const int n = p.seg.n[sg];
-    const long row = (long)(blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
-    if (row >= (long)p.B * n) return;
-    const float2 m = __ldg(p.seg.mk[sg] + row);
-    if (m.x == 0.0f && m.y == 0.0f) return;
-    float4 e = __ldg(p.seg.ev[sg] + row);
-    const int b = (int)(row / n);
-    const int dst = atomicAdd(p.sort.bins + bin_of(p.sort, sg, b, e.y, e.z), 1);
-    e.w = __int_as_float(b);
-    p.sort.ev[dst] = e;
-    p.sort.mk[dst] = m;
+    int sg, n; long row[kSortIlp], nrows;
+    if (!sort_rows(p, sg, n, row, nrows)) return;
+    float2 m[kSortIlp]; float4 e[kSortIlp]; int dst[kSortIlp];
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k) {
+        const bool ok = row[k] < nrows;
+        m[k] = ok ? __ldg(p.seg.mk[sg] + row[k]) : make_float2(0.f, 0.f);
+        e[k] = ok ? __ldg(p.seg.ev[sg] + row[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k) {
+        dst[k] = -1;
+        if (m[k].x == 0.0f && m[k].y == 0.0f) continue;
+        const int b = (int)(row[k] / n);
+        dst[k] = atomicAdd(p.sort.bins + bin_of(p.sort, sg, b, e[k].y, e[k].z), 1);
+        e[k].w = __int_as_float(b);
+    }
+#pragma unroll
+    for (int k = 0; k < kSortIlp; ++k)
+        if (dst[k] >= 0) { p.sort.ev[dst[k]] = e[k]; p.sort.mk[dst[k]] = m[k]; }
 }
 
 // ---- exclusive scan of the bins (int), three small kernels ------------------------------------------
@@ -116,7 +143,7 @@ using namespace tef;
 // Sort every segment of `p` (as laid out by fill_params) into p.sort.ev / p.sort.mk.  Afterwards
 // bins[i] holds the END of bin i, so segment s occupies rows [bins[first_bin(s)-1] (or 0), bins[last_bin(s)]).
 int tef_sort_events(const CmParams &p, cudaStream_t st) {
-    const int nblk = p.seg.blk_off[p.seg.nseg];
+    const int nblk = p.sort.blk_off[p.seg.nseg];
     const long nbins = p.sort.nbins;
     if (!p.sort.bins || !p.sort.sums || (nblk > 0 && (!p.sort.ev || !p.sort.mk))) return TEF_EINVAL;
     cudaMemsetAsync(p.sort.bins, 0, sizeof(int) * (nbins + 1), st);

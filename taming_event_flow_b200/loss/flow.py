@@ -20,10 +20,31 @@ from .._lib import CmDesc, check, lib, ptr, require_cuda, stream
 _MODES = {"one": 1, "two": 2, "four": 4}
 
 
+class _Workspace:
+    """Grow-only device buffers reused from one loss window to the next, so that a training loop allocates
+    nothing in steady state (the buffers are several hundred MB at DSEC resolution; going through the caching
+    allocator every step fragments it and stalls on cudaMalloc/cudaFree)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype or buf.device != device:
+            buf = torch.empty((max(n, 1),), dtype=dtype, device=device)
+            self.bufs[key] = buf
+        return buf[:n].view(shape)
+
+
 class _Window:
     """Device state of one loss window (between two `reset` calls)."""
 
-    def __init__(self):
+    def __init__(self, pool):
+        self.pool = pool       # the module's list of idle workspaces
+        self.ws = pool.pop() if pool else _Workspace()
         self.flows = []        # flows[t][f]: the caller's tensors (autograd leaves of the loss)
         self.packed = None     # [F,P,B,H,W,2]
         self.ev = ([], [])     # staged events per pass, (grad set, detached set)
@@ -34,6 +55,18 @@ class _Window:
         self.img = None
         self.den = None
         self.consumed = False
+
+    def release(self):
+        """Hand the workspace back (after backward, or when the window dies un-differentiated)."""
+        if self.ws is not None:
+            self.pool.append(self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class _CMLoss(torch.autograd.Function):
@@ -76,7 +109,8 @@ class BaseEventWarping(torch.nn.Module):
 
         self._passes = 0
         self._num_flows = None
-        self._win = _Window()
+        self._pool = []
+        self._win = _Window(self._pool)
 
         # timescales for loss computation (loss/flow.py:42-44)
         self.passes_loss = [config["data"]["passes_loss"] // (2 ** s) for s in range(config["data"]["scales_loss"])]
@@ -88,7 +122,8 @@ class BaseEventWarping(torch.nn.Module):
 
     def reset_base(self):
         self._passes = 0
-        self._win = _Window()      # a pending autograd graph keeps its own reference to the old window
+        self._win = None           # drop first: an un-differentiated window returns its workspace to the pool
+        self._win = _Window(self._pool)   # a pending autograd graph keeps its own reference to the old window
 
     def reset(self):
         self.reset_base()
@@ -100,6 +135,8 @@ class BaseEventWarping(torch.nn.Module):
     def update_base(self, flow_list):
         """Pack this pass' flow maps (upstream ``update_base``, loss/flow.py:46-66)."""
         w = self._win
+        if w.ws is None:
+            raise RuntimeError("update() after backward(): call reset() first (upstream resets after every loss, train_flow.py:136-137)")
         if self._num_flows is None:
             self._num_flows = len(flow_list)
         if len(flow_list) != self._num_flows:
@@ -114,7 +151,7 @@ class BaseEventWarping(torch.nn.Module):
         P = self._max_passes()
         if w.packed is None:
             w.shape = (F, B, H, W)
-            w.packed = torch.empty((F, P, B, H, W, 2), dtype=torch.float32, device=flow_list[0].device)
+            w.packed = w.ws.get("packed", (F, P, B, H, W, 2), torch.float32, flow_list[0].device)
         w.flows.append(list(flow_list))
         t = self._passes
         if t < P:
@@ -133,8 +170,9 @@ class BaseEventWarping(torch.nn.Module):
         if self.config["loss"]["round_ts"]:
             # event_ts[...] = event_ts.min() + 0.5 (:461-463); min() of an empty tensor raises, like upstream
             override = (events[:, :, 0].min() + float(self._passes) + 0.5).float().reshape(1)
-        ev_out = torch.empty((B, N, 4), dtype=torch.float32, device=events.device)
-        mk_out = torch.empty((B, N, 2), dtype=torch.float32, device=events.device)
+        t = len(w.ev[k])
+        ev_out = w.ws.get(("ev", k, t), (B, N, 4), torch.float32, events.device)
+        mk_out = w.ws.get(("mk", k, t), (B, N, 2), torch.float32, events.device)
         if rows > 0:
             if direct:
                 src, pass_index = events, float(self._passes)
@@ -179,13 +217,16 @@ class BaseEventWarping(torch.nn.Module):
         nslots, n_img, _, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp = (int(v) for v in sz)
         dev = w.packed.device
         i32, f32 = torch.int32, torch.float32
-        w.sort = (torch.empty((n_bins,), dtype=i32, device=dev), torch.empty((n_sums,), dtype=i32, device=dev),
-                  torch.empty((max(rows, 1), 4), dtype=f32, device=dev), torch.empty((max(rows, 1), 2), dtype=f32, device=dev),
-                  torch.empty((max(n_pos, 1),), dtype=f32, device=dev), torch.empty((max(F * rows_grad, 1),), dtype=i32, device=dev))
-        w.img = torch.empty((n_img,), dtype=f32, device=dev)
-        w.acc_sum = torch.empty((F, B, nslots), dtype=torch.float64, device=dev)
-        w.acc_nnz = torch.empty((F, B, nslots), dtype=i32, device=dev)
-        w.den = torch.empty((F, B, nslots), dtype=f32, device=dev)
+        if w.ws is None:
+            raise RuntimeError("this loss window has already been back-propagated; call reset() and update() again")
+        g = w.ws.get
+        w.sort = (g("bins", (n_bins,), i32, dev), g("sums", (n_sums,), i32, dev), g("sorted_ev", (max(rows, 1), 4), f32, dev),
+                  g("sorted_mk", (max(rows, 1), 2), f32, dev), g("posbuf", (max(n_pos, 1),), f32, dev),
+                  g("alive", (max(F * rows_grad, 1),), i32, dev))
+        w.img = g("img", (n_img,), f32, dev)
+        w.acc_sum = g("acc_sum", (F, B, nslots), torch.float64, dev)
+        w.acc_nnz = g("acc_nnz", (F, B, nslots), i32, dev)
+        w.den = g("den", (F, B, nslots), f32, dev)
         w.nslots = nslots
         loss = torch.empty((1,), dtype=f32, device=dev)
         self._fill_workspace(d, w)
@@ -207,8 +248,8 @@ class BaseEventWarping(torch.nn.Module):
         P = self._max_passes()
         d = self._desc(w)
         dev = w.packed.device
-        gpacked = torch.empty((F, P, B, 2, H, w.Wp, 2), dtype=torch.float32, device=dev)
-        grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)
+        gpacked = w.ws.get("gpacked", (F, P, B, 2, H, w.Wp, 2), torch.float32, dev)
+        grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)     # handed to autograd: not pooled
         g = gout.detach().float().contiguous().reshape(1)
         self._fill_workspace(d, w)
         d.gflow, d.grad_out = gpacked.data_ptr(), g.data_ptr()
@@ -216,6 +257,7 @@ class BaseEventWarping(torch.nn.Module):
         check(fn(ctypes.byref(d), stream()), "tef_linear_backward" if self._linear else "tef_iterative_backward")
         check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, stream()), "tef_unpack_flow_grad")
         w.consumed = True
+        w.release()                # stream order makes reuse by the next window safe
         return grads
 
     def images(self):
