@@ -49,6 +49,11 @@ WORKLOADS = {
     "linear_128x128_b8_f4": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Linear"),
     "linear_480x640_1Mev": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Linear"),
 }
+# BASELINE.json configs[1] / configs[3]: recurrent EV-FlowNet (PyTorch) + CM loss training step; metric = windows/s
+TRAIN_WORKLOADS = {
+    "train_128x128_b8": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative", scaling="weak"),
+    "train_128x128_gb64": dict(B=64, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative", scaling="strong"),
+}
 DEFAULT_WORKLOAD = "iterative_480x640_1Mev"
 
 
@@ -399,14 +404,96 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_train(args, wl, quiet=False):
+    """Training step of the recurrent EV-FlowNet (PyTorch/cuDNN) with the CM loss: P x (encode -> network -> update),
+    loss, backward through the loss kernels and the network, SUM all-reduce of the gradients, clip, Adam.
+    windows/s = global batch x P / step time."""
+    import torch.distributed as dist
+
+    from taming_event_flow_b200 import synthetic as syn
+    from taming_event_flow_b200.flownet import RecEVFlowNet
+    from taming_event_flow_b200.loss import flow as tef_flow
+    from taming_event_flow_b200.training import shard_range, train_step
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    own_pg = False
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+        own_pg = True
+    if wl["scaling"] == "strong":
+        a, b = shard_range(wl["B"], world, rank)
+        B_local, B_global = b - a, wl["B"]
+    else:
+        B_local, B_global = wl["B"], wl["B"] * world
+    wl_local = dict(wl, B=B_local)
+    seq = fast_sequence(500 + rank, wl_local)
+    P = wl["P"]
+    cfg = syn.loss_config(wl["H"], wl["W"], B_local, P, wl["S"], wl["mode"], warping=wl["warping"])
+    loss_fn = getattr(tef_flow, wl["warping"])(cfg, dev)
+    torch.manual_seed(0)
+    model = RecEVFlowNet(num_bins=2).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    nsteps = args.warmup + args.steps
+    masks = [(seq["masks"][t].to(dev), seq["d_masks"][t].to(dev)) for t in range(P)]
+    evs = [[(seq["events"][t].to(dev), seq["d_events"][t].to(dev)) for t in range(P)] for _ in range(nsteps)]
+
+    def step(i):
+        windows = [(evs[i][t][0], masks[t][0], evs[i][t][1], masks[t][1]) for t in range(P)]
+        return train_step(model, loss_fn, opt, windows, flow_scaling=32.0, clip_grad=100.0, world_size=world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    res = {"metric": "train_throughput", "value": B_global * P * args.steps / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch, 31.4M params)",
+                          optimizer="Adam lr 1e-5, clip 100, SUM all-reduce of gradients"),
+           "loss": float(loss.item()), "events_per_step": B_global * P * (wl["N"] + wl["Nd"])}
+    if own_pg:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not quiet:
+        print(json.dumps(res))
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     args = ap.parse_args()
+    if args.workload in TRAIN_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the CM-loss workloads only"}))
+            return
+        args.warmup = max(args.warmup, 3)
+        run_train(args, dict(TRAIN_WORKLOADS[args.workload], name=args.workload))
+        return
     wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":
         run_reference_arm(args, wl)

@@ -134,6 +134,8 @@ int tef_deblur_events(const float *flow, const float *events, const float *pol, 
 int tef_events_to_image(const float *xs, const float *ys, const float *ps, float *img, long n, int H, int W, int accumulate, void *stream);
 /* events_to_channels (:59-81): out [2][H][W] */
 int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, void *stream);
+/* batched events_to_channels over the loader's zero-padded [B][N][4] (ts, y, x, p) rows: out [B][2][H][W] */
+int tef_events_to_channels_batched(const float *events, float *out, int B, int N, int H, int W, void *stream);
 /* events_to_voxel (:32-56): out [bins][H][W] */
 int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
 

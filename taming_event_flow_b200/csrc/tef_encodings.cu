@@ -58,6 +58,22 @@ __global__ void __launch_bounds__(kThreads) to_voxel_kernel(const float *__restr
     }
 }
 
+// Batched variant of events_to_channels for the loader->network hand-off: rows are the
+// zero-padded [B][N][4] event tensor (ts, y, x, p) that custom_collate produces; padding rows have p = 0 and add nothing.
+__global__ void __launch_bounds__(kThreads) to_channels_batched_kernel(const float4 *__restrict__ ev, float *__restrict__ out, int B, int N, int H, int W) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (long)B * N) return;
+    const float4 e = ev[i];
+    const float p = e.w;
+    if (p == 0.f) return;
+    long px;
+    if (!pixel_of(e.z, e.y, H, W, px)) return;
+    const float mpos = p < 0.f ? 0.f : 1.f, mneg = p > 0.f ? 0.f : -1.f;
+    float *o = out + (long)(i / N) * 2 * H * W;
+    if (mpos != 0.f) red_add_f32(o + px, p * mpos);
+    if (mneg != 0.f) red_add_f32(o + (long)H * W + px, p * mneg);
+}
+
 }  // namespace tef
 
 using namespace tef;
@@ -90,5 +106,14 @@ extern "C" int tef_events_to_voxel(const float *xs, const float *ys, const float
     if (!xs || !ys || !ts || !ps) return TEF_EINVAL;
     ProfScope pr(K_ENCODING, ST);
     to_voxel_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(xs, ys, ts, ps, out, n, bins, H, W);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_events_to_channels_batched(const float *events, float *out, int B, int N, int H, int W, void *stream) {
+    if (B < 1 || N < 0 || H < 1 || W < 1 || !out) return TEF_EINVAL;
+    cudaMemsetAsync(out, 0, sizeof(float) * (long)B * 2 * H * W, ST);
+    if (N == 0) return 0;
+    if (!events) return TEF_EINVAL;
+    ProfScope pr(K_ENCODING, ST);
+    to_channels_batched_kernel<<<TEF_GRID((long)B * N), kThreads, 0, ST>>>((const float4 *)events, out, B, N, H, W);
     return (int)cudaGetLastError();
 }

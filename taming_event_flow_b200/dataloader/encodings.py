@@ -49,3 +49,16 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
     out = torch.empty((2, H, W), dtype=torch.float32, device=xs.device)
     check(lib().tef_events_to_channels(ptr(xs), ptr(ys), ptr(ps), ptr(out), _l(xs.numel()), H, W, stream()), "tef_events_to_channels")
     return out
+
+
+def events_to_channels_batched(event_list, sensor_size):
+    """``events_to_channels`` for a whole zero-padded batch ``[B x N x 4]`` of (ts, y, x, p) rows in one launch:
+    ``[B x 2 x H x W]``.  Not an upstream function: it replaces the per-sample loop + host round trip of the loader
+    (upstream ``dataloader/base.py:164-167,291``); padding rows (p = 0) add nothing."""
+    require_cuda(event_list)
+    ev = event_list.contiguous().float()
+    B, N = ev.shape[0], ev.shape[1]
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((B, 2, H, W), dtype=torch.float32, device=ev.device)
+    check(lib().tef_events_to_channels_batched(ptr(ev), ptr(out), B, N, H, W, stream()), "tef_events_to_channels_batched")
+    return out

@@ -1,0 +1,94 @@
+"""Recurrent EV-FlowNet in plain PyTorch, for the training-step workloads of ``bench.py`` / ``train_synthetic.py``.
+
+``north_star`` keeps the flow networks on PyTorch (cuDNN convolutions); this module is NOT part of the accelerated path.
+It re-states the topology of upstream ``RecEVFlowNet`` (``models/model.py:6-85``, ``models/arch.py:177-242``,
+``models/submodules.py``) so that the synthetic training step has the same cost and parameter count
+(31,365,352 parameters with 2 input channels):
+
+    4 x [3x3 stride-2 conv + ReLU -> ConvGRU]   channels 64, 128, 256, 512
+    2 x residual block at 512 channels
+    4 x [skip (sum) -> (concat previous 2-ch prediction) -> bilinear x2 -> 3x3 conv + ReLU]   256, 128, 64, 32
+    a 1x1 tanh flow head after every decoder, each prediction up-sampled to the input size and scaled by 2^(3-i)
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _conv(cin, cout, k, stride=1, w_scale=None):
+    conv = nn.Conv2d(cin, cout, k, stride, k // 2)
+    s = math.sqrt(1.0 / cin) if w_scale is None else w_scale
+    nn.init.uniform_(conv.weight, -s, s)
+    nn.init.zeros_(conv.bias)
+    return conv
+
+
+class ConvGRUCell(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.gate_z, self.gate_r, self.gate_c = (nn.Conv2d(2 * channels, channels, 3, padding=1) for _ in range(3))
+        for g in (self.gate_z, self.gate_r, self.gate_c):
+            nn.init.orthogonal_(g.weight)
+            nn.init.zeros_(g.bias)
+
+    def forward(self, x, h):
+        if h is None:
+            h = torch.zeros_like(x)
+        xh = torch.cat([x, h], 1)
+        z = torch.sigmoid(self.gate_z(xh))
+        r = torch.sigmoid(self.gate_r(xh))
+        cand = torch.tanh(self.gate_c(torch.cat([x, h * r], 1)))
+        return h * (1 - z) + cand * z
+
+
+class RecEVFlowNet(nn.Module):
+    def __init__(self, num_bins=2, base_channels=64, num_encoders=4, final_w_scale=0.01):
+        super().__init__()
+        chans = [base_channels * 2 ** i for i in range(num_encoders)]            # 64 128 256 512
+        ins = [num_bins] + chans[:-1]
+        self.enc_conv = nn.ModuleList([_conv(i, o, 3, stride=2) for i, o in zip(ins, chans)])
+        self.enc_gru = nn.ModuleList([ConvGRUCell(o) for o in chans])
+        self.res = nn.ModuleList([nn.ModuleList([_default_conv(chans[-1]), _default_conv(chans[-1])]) for _ in range(2)])
+        dec_in = list(reversed(chans))                                           # 512 256 128 64
+        dec_out = [c // 2 for c in dec_in]                                       # 256 128 64 32
+        self.dec = nn.ModuleList([_conv(i + (0 if k == 0 else 2), o, 3) for k, (i, o) in enumerate(zip(dec_in, dec_out))])
+        self.heads = nn.ModuleList([_conv(o, 2, 1, w_scale=final_w_scale) for o in dec_out])
+        self.num_encoders = num_encoders
+        self.states = [None] * num_encoders
+
+    def reset_states(self):
+        self.states = [None] * self.num_encoders
+
+    def detach_states(self):
+        self.states = [None if s is None else s.detach() for s in self.states]
+
+    def forward(self, x):
+        H, W = x.shape[2], x.shape[3]
+        skips = []
+        for i in range(self.num_encoders):
+            x = torch.relu(self.enc_conv[i](x))
+            x = self.enc_gru[i](x, self.states[i])
+            self.states[i] = x
+            skips.append(x)
+        for c1, c2 in self.res:
+            x = torch.relu(x + c2(torch.relu(c1(x))))
+        flows, pred = [], None
+        for i in range(self.num_encoders):
+            x = x + skips[self.num_encoders - 1 - i]
+            if pred is not None:
+                x = torch.cat([pred, x], 1)
+            x = torch.relu(self.dec[i](F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)))
+            pred = torch.tanh(self.heads[i](x))
+            up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
+            flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
+        return {"flow": flows}
+
+
+def _default_conv(c):
+    return nn.Conv2d(c, c, 3, padding=1)
+
+
+def count_parameters(m):
+    return sum(p.numel() for p in m.parameters())

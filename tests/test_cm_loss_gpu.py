@@ -195,3 +195,38 @@ def test_round_ts_and_loss_scaling_off():
     o = orc.linear(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
     assert abs(g["loss"] - o["loss"]) <= TOL * abs(o["loss"])
     assert rel_err(g["gflow"], o["gflow"])[0] < TOL
+
+
+def test_train_step_with_network():
+    """The loss drives a (small) training loop: gradients reach the network parameters and the loss is finite."""
+    from taming_event_flow_b200.flownet import RecEVFlowNet, count_parameters
+    from taming_event_flow_b200.loss.flow import Iterative
+    from taming_event_flow_b200.training import train_step
+
+    B, P, N, H, W = 2, 4, 1500, 64, 64
+    seq = syn.make_sequence(21, B, P, N, 500, H, W, 1, 1.0)
+    torch.manual_seed(0)
+    model = RecEVFlowNet(num_bins=2, base_channels=8).cuda()
+    assert count_parameters(RecEVFlowNet(2)) == 31365352            # upstream RecEVFlowNet with 2 input channels (SURVEY.md §8d)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    loss_fn = Iterative(syn.loss_config(H, W, B, P), "cuda")
+    before = [p.detach().clone() for p in model.parameters()]
+    losses = []
+    for it in range(3):
+        windows = [(seq["events"][t].cuda().clone(), seq["masks"][t].cuda(), seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda()) for t in range(P)]
+        losses.append(train_step(model, loss_fn, opt, windows).item())
+    assert all(np.isfinite(losses))
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+def test_events_to_channels_batched_matches_per_sample():
+    from taming_event_flow_b200.dataloader.encodings import events_to_channels, events_to_channels_batched
+
+    B, N, H, W = 3, 4000, 48, 64
+    g = torch.Generator().manual_seed(2)
+    ev, _ = syn.make_window(g, B, N, H, W, ragged=True)
+    out = events_to_channels_batched(ev.cuda(), (H, W))
+    for b in range(B):
+        n = int((ev[b, :, 3] != 0).sum())
+        ref = events_to_channels(ev[b, :n, 2].cuda(), ev[b, :n, 1].cuda(), ev[b, :n, 3].cuda(), (H, W))
+        assert torch.equal(out[b], ref)
