@@ -65,14 +65,13 @@ typedef struct tef_cm_desc {
     /* workspace written by the forward call and read by the backward call (sizes from tef_cm_sizes) */
     void *sort_bins;       /* int [nbins + 1]  tile-sort histogram / offsets           */
     void *sort_sums;       /* int scan scratch                                         */
-    void *sorted_ev;       /* float4 [rows]: (ts, y, x, sample index bits), tile-sorted */
-    void *sorted_mk;       /* float2 [rows]                                            */
+    void *sorted_ev;       /* 32-byte records [rows]: (ts, y, x, sample index bits, mask+, mask-, 0, 0), tile-sorted */
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
     void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
 } tef_cm_desc;
 
 /* buffer sizes for the events currently described by `d`; out[9] =
-   { slots, floats in img, floats in gflow, ints in sort_bins, ints in sort_sums, rows of sorted_ev/sorted_mk,
+   { slots, floats in img, floats in gflow, ints in sort_bins, ints in sort_sums, rows of sorted_ev,
      gradient-carrying rows, floats in posbuf, padded row length Wp } */
 int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out);
 

@@ -48,7 +48,6 @@ class CmDesc(ctypes.Structure):
             ("sort_bins", ctypes.c_void_p),
             ("sort_sums", ctypes.c_void_p),
             ("sorted_ev", ctypes.c_void_p),
-            ("sorted_mk", ctypes.c_void_p),
             ("posbuf", ctypes.c_void_p),
             ("alivebuf", ctypes.c_void_p),
         ]

@@ -26,8 +26,7 @@ struct SortGeom {
     long nbins;                      // nseg * B * tiles * 128
     int *bins;                       // [nbins + 1] histogram -> offsets -> bin ends
     int *sums;                       // scan scratch, one int per 2048 bins
-    float4 *ev;                      // sorted rows (ts, y, x, sample index as int bits)
-    float2 *mk;
+    float4 *rec;                     // sorted rows, 32 B each: (ts, y, x, sample index bits | mask+, mask-, 0, 0)
 };
 
 // One entry per temporal scale (loss/flow.py:42-44, :434-441, :657-668)
@@ -137,7 +136,7 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     for (int s = 0; s < ns; ++s) g.blk_off[s + 1] = g.blk_off[s] + (int)(((long)d->B * p.seg.n[s] + kThreads * 4 - 1) / (kThreads * 4));
     g.nbins = (long)ns * d->B * g.tiles * 128;
     g.bins = (int *)d->sort_bins; g.sums = (int *)d->sort_sums;
-    g.ev = (float4 *)d->sorted_ev; g.mk = (float2 *)d->sorted_mk;
+    g.rec = (float4 *)d->sorted_ev;
     return 0;
 }
 
@@ -165,8 +164,11 @@ __device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b,
     seg_rows(p, sg, lo, hi);
     row = lo + (blk - p.seg.blk_off[sg]) * kThreads + threadIdx.x;
     if (row >= hi) return false;
-    e = __ldg(p.sort.ev + row);
-    m = __ldg(p.sort.mk + row);
+    float m2, m3;
+    // one 256-bit load per event (LDG.E.ENL2.256): the whole 32-byte sorted record
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w), "=f"(m.x), "=f"(m.y), "=f"(m2), "=f"(m3)
+                 : "l"(p.sort.rec + 2 * (long)row));
     b = __float_as_int(e.w);
     return true;
 }

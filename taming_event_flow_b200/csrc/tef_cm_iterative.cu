@@ -286,7 +286,7 @@ extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
     CmParams p;
     int rc = fill_params(d, 0, p);                 // same segment / bin layout as the forward call
     if (rc) return rc;
-    if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.ev || !p.sort.mk) return TEF_EINVAL;
+    if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
     if (p.rows_grad > 0 && (!p.posbuf || !p.alivebuf)) return TEF_EINVAL;
     grad_segments_only(p);
     cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * 2 * p.ig.plane, st);

@@ -220,9 +220,8 @@ class BaseEventWarping(torch.nn.Module):
         if w.ws is None:
             raise RuntimeError("this loss window has already been back-propagated; call reset() and update() again")
         g = w.ws.get
-        w.sort = (g("bins", (n_bins,), i32, dev), g("sums", (n_sums,), i32, dev), g("sorted_ev", (max(rows, 1), 4), f32, dev),
-                  g("sorted_mk", (max(rows, 1), 2), f32, dev), g("posbuf", (max(n_pos, 1),), f32, dev),
-                  g("alive", (max(F * rows_grad, 1),), i32, dev))
+        w.sort = (g("bins", (n_bins,), i32, dev), g("sums", (n_sums,), i32, dev), g("sorted_ev", (max(rows, 1), 8), f32, dev),
+                  g("posbuf", (max(n_pos, 1),), f32, dev), g("alive", (max(F * rows_grad, 1),), i32, dev))
         w.img = g("img", (n_img,), f32, dev)
         w.acc_sum = g("acc_sum", (F, B, nslots), torch.float64, dev)
         w.acc_nnz = g("acc_nnz", (F, B, nslots), i32, dev)
@@ -238,7 +237,7 @@ class BaseEventWarping(torch.nn.Module):
 
     @staticmethod
     def _fill_workspace(d, w):
-        d.sort_bins, d.sort_sums, d.sorted_ev, d.sorted_mk, d.posbuf, d.alivebuf = (x.data_ptr() for x in w.sort)
+        d.sort_bins, d.sort_sums, d.sorted_ev, d.posbuf, d.alivebuf = (x.data_ptr() for x in w.sort)
         d.img, d.den = w.img.data_ptr(), w.den.data_ptr()
 
     def _backward_kernels(self, w, gout):
