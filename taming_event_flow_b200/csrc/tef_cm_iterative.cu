@@ -164,55 +164,40 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     const uint32_t alive = p.alivebuf[(long)f * p.rows_grad + row];
     const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
 
-    // scales whose sub-window takes this event, and the range of nodes that receive an image gradient.
-    // Scale 0 (the only one in the shipped configs) is kept in registers; further scales are re-derived per node.
+    // scales whose sub-window takes this event, and the range of nodes that receive an image gradient
     int lo_node = p.P + 1, hi_node = -1;
     uint32_t has = 0;
-    Win w0;
-    float rd0 = 0.f;
     for (int s = 0; s < p.sc.S; ++s) {
         Win w;
         if (!window_of(p, s, t, alive, w)) continue;
         if (p.border && !w.shared_ok) continue;
         has |= 1u << s;
-        if (s == 0) { w0 = w; rd0 = 1.0f / (float)w.delta; }
         lo_node = min(lo_node, max(w.low_tref, t - w.delta + 1));
         hi_node = max(hi_node, min(w.high_tref - 1, t + w.delta));
     }
     if (!has) return;
     const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
-    const long slot_stride = 4 * p.ig.plane;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
-        if ((has & 1u) && feeds(w0, tr, t)) {
-            const float nts = 1.0f - div_const(fabsf((float)tr - ts), (float)w0.delta, rd0);
-            iwe_grad<true>(img_fb + (long)(w0.slot0 + tr) * slot_stride, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
-        }
-        if (has >> 1) {
-            for (int s = 1; s < p.sc.S; ++s) {
-                if (!((has >> s) & 1u)) continue;
-                Win w;
-                window_of(p, s, t, alive, w);
-                if (!feeds(w, tr, t)) continue;
-                const float fdelta = (float)w.delta;
-                const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
-                iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * slot_stride, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
-            }
+        for (int s = 0; s < p.sc.S; ++s) {
+            if (!((has >> s) & 1u)) continue;
+            Win w;
+            window_of(p, s, t, alive, w);
+            if (!feeds(w, tr, t)) continue;
+            const float fdelta = (float)w.delta;
+            const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
+            iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
 
-    const long map_stride = (long)p.B * HW, gmap_stride = (long)p.B * 2 * p.ig.plane;
     // reverse of the forward chain: nodes hi_node .. t+1 (nodes beyond carry no gradient)
     float cy_ = 0.f, cx_ = 0.f;
     {
         int tr = min(hi_node, p.P);
-        const float2 *pq = pb + (long)tr * p.rows_grad;                  // position of node tr; pq - rows_grad: node tr-1
-        const float2 *map = flow_f + (long)(tr - 1) * map_stride + (long)b * HW;
-        float2 *gmap = gflow_f + (long)(tr - 1) * gmap_stride + (long)b * 2 * p.ig.plane;
-        float2 q = (tr >= t + 1) ? *pq : make_float2(0.f, 0.f);
-        for (; tr >= t + 1; --tr, pq -= p.rows_grad, map -= map_stride, gmap -= gmap_stride) {
+        float2 q = (tr >= t + 1) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        for (; tr >= t + 1; --tr) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(y0, x0) : *(pq - p.rows_grad);
+            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr - 1) * p.rows_grad];
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -220,7 +205,8 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : 1.0f;
-                step_bwd(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                const long mo = (long)(tr - 1) * p.B + b;
+                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
@@ -229,13 +215,10 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     cy_ = 0.f; cx_ = 0.f;
     {
         int tr = max(lo_node, 0);
-        const float2 *pq = pb + (long)tr * p.rows_grad;
-        const float2 *map = flow_f + (long)tr * map_stride + (long)b * HW;
-        float2 *gmap = gflow_f + (long)tr * gmap_stride + (long)b * 2 * p.ig.plane;
-        float2 q = (tr <= t) ? *pq : make_float2(0.f, 0.f);
-        for (; tr <= t; ++tr, pq += p.rows_grad, map += map_stride, gmap += gmap_stride) {
+        float2 q = (tr <= t) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        for (; tr <= t; ++tr) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(y0, x0) : *(pq + p.rows_grad);
+            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr + 1) * p.rows_grad];
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -243,7 +226,8 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : -1.0f;
-                step_bwd(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                const long mo = (long)tr * p.B + b;
+                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
