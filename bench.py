@@ -333,28 +333,60 @@ def run_ours(args, wl):
     h2d = sum(t.numel() * 4 for per in h_flows for t in per) + sum(t.numel() * 4 for lst in (h_masks, h_dmasks, h_ev, h_dev) for t in lst)
     d2h = h_grads.numel() * 4 + 4
 
-    def step_e2e():
+    # Double-buffered like a prefetching loader: the H2D copies of step i+1 run on a copy stream while step i computes;
+    # every copy of every step is still inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    slots = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])          # the step that used this slot has finished with it
+            slots[k] = ([[f.to(dev, non_blocking=True) for f in per] for per in h_flows],
+                        [e.to(dev, non_blocking=True) for e in h_ev], [m.to(dev, non_blocking=True) for m in h_masks],
+                        [e.to(dev, non_blocking=True) for e in h_dev], [m.to(dev, non_blocking=True) for m in h_dmasks])
+            ready[k].record(copy_stream)
+
+    def step_e2e(i, last):
+        k = i % 2
+        if not last:
+            prefetch((i + 1) % 2)
+        main_stream.wait_event(ready[k])
+        fl_d, ev_d, mk_d, dev_d, dmk_d = slots[k]
+        for lst in (ev_d, mk_d, dev_d, dmk_d):
+            for x in lst:
+                x.record_stream(main_stream)
         module.reset()
         flows = []
         for t in range(P):
-            fl = [f.to(dev, non_blocking=True).requires_grad_(True) for f in h_flows[t]]
+            fl = [f.requires_grad_(True) for f in fl_d[t]]
+            for f in fl:
+                f.record_stream(main_stream)
             flows.append(fl)
-            module.update(fl, h_ev[t].to(dev, non_blocking=True), h_masks[t].to(dev, non_blocking=True),
-                          h_dev[t].to(dev, non_blocking=True), h_dmasks[t].to(dev, non_blocking=True))
+            module.update(fl, ev_d[t], mk_d[t], dev_d[t], dmk_d[t])
         loss = module()
         loss.backward()
         for t in range(P):
             for f in range(F):
                 h_grads[t, f].copy_(flows[t][f].grad, non_blocking=True)
         h_loss.copy_(loss.detach(), non_blocking=True)
+        consumed[k].record(main_stream)
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_e2e()
+    for k in range(2):
+        consumed[k].record(main_stream)
+    prefetch(0)
+    for i in range(2):
+        step_e2e(i, False)
     barrier()
+    # restart the pipeline so that the first timed step pays its own (un-overlapped) upload
+    torch.cuda.synchronize()
     e0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
+    prefetch(0)
+    for i in range(e2e_steps):
+        step_e2e(i, i == e2e_steps - 1)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
