@@ -138,6 +138,10 @@ int tef_events_to_channels_batched(const float *events, float *out, int B, int N
 /* events_to_voxel (:32-56): out [bins][H][W] */
 int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
 
+/* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers;
+   mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */
+int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* launch accounting / per-kernel timing (used by bench.py for gpu_launches   */
 /* and the roofline; CUDA events are recorded on the launching stream)        */

@@ -1,0 +1,56 @@
+// tef_microbench.cu -- measures the two rates that actually bound the CM kernels on this GPU (SURVEY.md §8d asks for a
+// measured atomic peak): 16-byte vector reductions (red.global.add.v4.f32) and 8-byte gathers, both on an L2-resident
+// buffer, with uniformly random addresses ("spread") or addresses confined to a 4 KB window per warp ("local", what
+// tile-sorted events produce).  bench.py runs them once, outside the timed region, and reports the CM kernels' achieved
+// lane-op rates against them.
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+__device__ __forceinline__ uint32_t lcg(uint32_t &s) { s = s * 1664525u + 1013904223u; return s; }
+
+// mode 0: spread, 1: local.  slots = number of float4 slots in buf (power of two)
+__global__ void __launch_bounds__(kThreads) mb_red_kernel(float4 *buf, uint32_t slots, int iters, int mode) {
+    uint32_t s = (blockIdx.x * kThreads + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t warp_base = ((blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 40503u * 256u) & (slots - 1);
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t r = lcg(s) >> 8;
+        const uint32_t a = mode == 0 ? (r & (slots - 1)) : ((warp_base + (r & 255u) + (uint32_t)i * 64u) & (slots - 1));
+        red_add_v4(reinterpret_cast<float2 *>(buf + a), 1.0f, 0.5f, 0.25f, 0.125f);
+    }
+}
+__global__ void __launch_bounds__(kThreads) mb_gather_kernel(const float2 *__restrict__ buf, uint32_t slots, int iters, int mode, float *sink) {
+    uint32_t s = (blockIdx.x * kThreads + threadIdx.x) * 2654435761u + 777u;
+    const uint32_t warp_base = ((blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 40503u * 512u) & (slots - 1);
+    float acc = 0.f;
+    for (int i = 0; i < iters; i += 4) {
+        float2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t r = lcg(s) >> 8;
+            const uint32_t a = mode == 0 ? (r & (slots - 1)) : ((warp_base + (r & 511u) + (uint32_t)(i + k) * 128u) & (slots - 1));
+            v[k] = __ldg(buf + a);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += v[k].x + v[k].y;
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+}  // namespace tef
+
+using namespace tef;
+
+// kind 0: red.v4, kind 1: 8-byte gather.  buf: at least `bytes` (power of two) of device memory.  Launches
+// 148*8 CTAs x 256 threads x iters operations; returns 0 and the operation count through *ops.
+extern "C" int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream) {
+    if (!buf || bytes < (1 << 20) || (bytes & (bytes - 1)) || iters < 4) return TEF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = 148 * 8;
+    ProfScope ps(K_MICROBENCH, st);
+    if (kind == 0) mb_red_kernel<<<ctas, kThreads, 0, st>>>((float4 *)buf, (uint32_t)(bytes / 16), iters, mode);
+    else mb_gather_kernel<<<ctas, kThreads, 0, st>>>((const float2 *)buf, (uint32_t)(bytes / 8), iters & ~3, mode, (float *)buf);
+    if (ops) *ops = (long)ctas * kThreads * (kind == 0 ? iters : (iters & ~3));
+    return (int)cudaGetLastError();
+}
