@@ -54,6 +54,12 @@ TRAIN_WORKLOADS = {
     "train_128x128_b8": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative", scaling="weak"),
     "train_128x128_gb64": dict(B=64, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative", scaling="strong"),
 }
+# BASELINE.json configs[2]: sequential inference at DSEC resolution with the events_to_voxel encoding (5 bins)
+INFER_WORKLOADS = {
+    "inference_480x640_100kev": dict(N=100_000, H=480, W=640, bins=5),
+    "inference_480x640_500kev": dict(N=500_000, H=480, W=640, bins=5),
+    "inference_480x640_1Mev": dict(N=1_000_000, H=480, W=640, bins=5),
+}
 DEFAULT_WORKLOAD = "iterative_480x640_1Mev"
 
 
@@ -562,14 +568,89 @@ def run_train(args, wl, quiet=False):
     return res
 
 
+def run_inference(args, wl):
+    """Sequential inference (eval_flow.py:70-90): per window, events_to_voxel (our kernel) + recurrent network forward
+    (PyTorch), batch 1, no gradients.  Reports windows/s, the per-window latency split and the encoding kernel's HBM roofline."""
+    import ctypes
+
+    from taming_event_flow_b200 import _lib
+    from taming_event_flow_b200.dataloader.encodings import events_to_voxel
+    from taming_event_flow_b200.flownet import RecEVFlowNet
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    H, W, N, bins = wl["H"], wl["W"], wl["N"], wl["bins"]
+    g = torch.Generator().manual_seed(3)
+    nwin = 16
+    wins = []
+    for _ in range(nwin):
+        ts, _ = torch.sort(torch.rand(N, generator=g))
+        ts = (ts - ts[0]) / (ts[-1] - ts[0])
+        wins.append(tuple(t.to(dev) for t in (torch.randint(0, W, (N,), generator=g).float(), torch.randint(0, H, (N,), generator=g).float(), ts,
+                                              (torch.randint(0, 2, (N,), generator=g) * 2 - 1).float())))
+    torch.manual_seed(0)
+    model = RecEVFlowNet(num_bins=bins).to(dev).eval()
+    L = _lib.lib()
+
+    def window(i, net=True):
+        xs, ys, ts, ps = wins[i % nwin]
+        vox = events_to_voxel(xs, ys, ts, ps, bins, (H, W))
+        return model(vox.unsqueeze(0))["flow"][-1] if net else vox
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.no_grad():
+        for i in range(args.warmup):
+            window(i)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(args.steps):
+            window(i, net=False)
+        ev[1].record()
+        torch.cuda.synchronize()
+        L.tef_prof_reset(); L.tef_prof_enable(1)
+        ev[2].record()
+        for i in range(args.steps):
+            window(i)
+        ev[3].record()
+        torch.cuda.synchronize()
+        L.tef_prof_enable(0)
+    tot, timed, cnt = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+    L.tef_prof_name.restype = ctypes.c_char_p
+    kid = [k for k in range(L.tef_prof_num_kernels()) if L.tef_prof_name(k) == b"encoding_kernels"][0]
+    L.tef_prof_read(kid, ctypes.byref(tot), ctypes.byref(timed), ctypes.byref(cnt))
+    enc_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    tot_ms = ev[2].elapsed_time(ev[3]) / args.steps
+    k_ms = tot.value / max(timed.value, 1)
+    nbytes = 16 * N + 4 * bins * H * W
+    hbm = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        hbm = float(json.load(open(pk)).get("hbm_gbs", hbm))
+    print(json.dumps({
+        "metric": "inference_throughput", "value": 1e3 / tot_ms, "unit": "windows/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "events_per_window": N, "resolution": [H, W], "num_bins": bins, "network": "RecEVFlowNet (PyTorch fp32 eager)"},
+        "latency_ms": {"encode_call": enc_ms, "encode_kernel": k_ms, "network_forward": tot_ms - enc_ms, "window": tot_ms},
+        "encode_Mevents_per_s": N / (enc_ms * 1e-3) / 1e6,
+        "roofline": {"bound": "hbm", "kernel": "to_voxel_kernel", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "algorithmic_bytes_per_launch": nbytes}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + sorted(INFER_WORKLOADS))
     args = ap.parse_args()
+    if args.workload in INFER_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the CM-loss workloads only"}))
+            return
+        args.warmup = max(args.warmup, 3)
+        run_inference(args, dict(INFER_WORKLOADS[args.workload], name=args.workload))
+        return
     if args.workload in TRAIN_WORKLOADS:
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the CM-loss workloads only"}))

@@ -46,7 +46,8 @@ typedef struct tef_cm_desc {
     int mode;              /* iterative_mode: 1 one, 2 two, 4 four (ignored by Linear) */
     int border_comp;       /* BaseEventWarping.border_compensation                    */
     int loss_scaling;      /* BaseEventWarping.loss_scaling                           */
-    int deterministic;     /* 0: fp32 RED accumulation; 1: order-independent fixed point (bit-reproducible) */
+    int deterministic;     /* 0: fp32 vector reductions; 1: 64-bit fixed-point (2^-40) integer reductions -- order-independent,
+                              bit-reproducible; img / gflow then hold int64 instead of float (twice the bytes)  */
     /* staged events, set 0 = with gradient, set 1 = detached; pass t holds [B][n] rows:
        ev = float4 (ts + t, y, x, p), mk = float2 (pos, neg).  Written by tef_stage_events. */
     const void *ev[2][TEF_MAX_PASSES];
@@ -57,8 +58,8 @@ typedef struct tef_cm_desc {
     void *img;             /* accumulation images, float2 (count, time-weighted): [F][B][slots][phase][pol][H][Wp];
                               pixel x lives at column x of phase 0 plus column x+1 of phase 1 (see csrc/tef_cm_common.cuh);
                               after backward the phase-0 planes hold (dL/dcount, dL/dtime-weighted)              */
-    double *acc_sum;       /* [F][B][slots] sum of squared normalised timestamps       */
-    int *acc_nnz;          /* [F][B][slots] pixels with at least one event             */
+    double *acc_sum;       /* [F][B][slots][chunks] partial sums of squared normalised timestamps (fixed-order reduction) */
+    int *acc_nnz;          /* [F][B][slots][chunks] partial counts of pixels with at least one event */
     float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
     float *loss;           /* [1] scalar loss                                          */
     const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
@@ -68,11 +69,13 @@ typedef struct tef_cm_desc {
     void *sorted_ev;       /* 32-byte records [rows]: (ts, y, x, sample index bits, mask+, mask-, 0, 0), tile-sorted */
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
     void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
+    void *gimg;            /* deterministic mode only: gradient images float2 [F][B][slots][pol][H][Wp] */
 } tef_cm_desc;
 
-/* buffer sizes for the events currently described by `d`; out[9] =
+/* buffer sizes for the events currently described by `d`; out[11] =
    { slots, floats in img, floats in gflow, ints in sort_bins, ints in sort_sums, rows of sorted_ev,
-     gradient-carrying rows, floats in posbuf, padded row length Wp } */
+     gradient-carrying rows, floats in posbuf, padded row length Wp, chunks per image (acc_sum / acc_nnz),
+     floats in gimg } */
 int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out);
 
 /* Iterative.update / Linear.update, event part (loss/flow.py:456-473, :246-263):
@@ -87,7 +90,7 @@ int tef_stage_events(void *events_inout, const void *pol_mask, void *ev_out, voi
 int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B, int H, int W,
                   void *packed, void *stream);
 /* backward counterpart: packed gradient -> [P][F][B][2][H][W] */
-int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, void *stream);
+int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream);
 
 /* Iterative.forward (loss/flow.py:588-746) and its analytic backward */
 int tef_iterative_forward(const tef_cm_desc *d, void *stream);

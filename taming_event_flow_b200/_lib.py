@@ -50,6 +50,7 @@ class CmDesc(ctypes.Structure):
             ("sorted_ev", ctypes.c_void_p),
             ("posbuf", ctypes.c_void_p),
             ("alivebuf", ctypes.c_void_p),
+            ("gimg", ctypes.c_void_p),
         ]
     )
 

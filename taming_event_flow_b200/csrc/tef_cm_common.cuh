@@ -49,13 +49,24 @@ struct ImgGeom {
     long plane;      // H * Wp
 };
 
+// Deterministic mode: every accumulation (images, flow-gradient maps) is done in 64-bit fixed point (2^-40 resolution)
+// with integer reductions, which are associative, so results are bit-reproducible run to run and independent of the
+// event order; the per-image reductions use fixed-order partial sums in both modes.
+constexpr double kFixScale = 1099511627776.0;      // 2^40
+__device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * kFixScale); }
+__device__ __forceinline__ float from_fix(long long v) { return (float)((double)v * (1.0 / kFixScale)); }
+__device__ __forceinline__ void red_add_i64(long long *addr, long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
 struct CmParams {
-    int B, H, W, P, F, mode, border, loss_scaling, nslots, linear;
+    int B, H, W, P, F, mode, border, loss_scaling, nslots, linear, det, nchunks;
     Res res;
     ImgGeom ig;
     const float2 *flow;
     float2 *gflow;
-    float2 *img;
+    float2 *img;             // deterministic mode: same layout with every float replaced by an int64 (twice the bytes)
+    float2 *gimg;            // deterministic mode: gradient images [F][B][slot][pol][H][Wp] float2 (otherwise in place in img)
     float2 *posbuf;          // [(P+1)][rows_grad] chain positions of the gradient-carrying rows (Iterative)
     uint32_t *alivebuf;      // [F][rows_grad] cumulative in-image bits (bit tref)
     long rows_grad;
@@ -106,7 +117,9 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     int rc = check_desc(d, linear);
     if (rc) return rc;
     p.B = d->B; p.H = d->H; p.W = d->W; p.P = d->P; p.F = d->F; p.mode = d->mode;
-    p.border = d->border_comp; p.loss_scaling = d->loss_scaling; p.linear = linear;
+    p.border = d->border_comp; p.loss_scaling = d->loss_scaling; p.linear = linear; p.det = d->deterministic ? 1 : 0;
+    p.nchunks = (int)(((long)d->H * d->W + 2047) / 2048);
+    p.gimg = (float2 *)d->gimg;
     p.res = Res::make(d->H, d->W);
     p.flow = (const float2 *)d->flow; p.gflow = (float2 *)d->gflow; p.img = (float2 *)d->img;
     p.ig.Wp = (d->W + 3) & ~1; p.ig.plane = (long)d->H * p.ig.Wp;
@@ -197,7 +210,7 @@ __device__ __forceinline__ float2 *img_plane(float2 *slot_base, const ImgGeom &g
 // (w_left, w_left*n, w_right, w_right*n) into the plane of the event's polarity.
 // Corner coordinates, weights and in-image tests are exactly get_interpolation's (utils/iwe.py:85-107);
 // a corner outside the image (or with weight 0) contributes an exact +0.
-template <bool INSIDE>
+template <bool INSIDE, bool DET>
 __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts, float2 m) {
     Corners c;
     corners<INSIDE>(y, x, r, c);
@@ -216,8 +229,23 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
         if (wl == 0.0f && wr == 0.0f) continue;
         const int off = (int)c.cy[ky] * g.Wp + col;
         const float tl = wl * nts, tr = wr * nts;
-        red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
-        if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
+        if (!DET) {
+            red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
+            if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
+        } else {
+            for (int q = pol; q < (both ? 2 : pol + 1); ++q) {
+                const float mq = q ? m.y : m.x;
+                long long *dst = reinterpret_cast<long long *>(slot_base) + ((long)(phase * 2 + q) * g.plane + off) * 2;
+                const float v[4] = { wl * mq, tl * mq, wr * mq, tr * mq };
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (v[k] == 0.0f) continue;
+                    long long f = to_fix(v[k]);
+                    if (f == 0) f = v[k] > 0.0f ? 1 : -1;           // a non-zero contribution stays non-zero (nnz of focus_loss)
+                    red_add_i64(dst + k, f);
+                }
+            }
+        }
     }
 }
 
@@ -231,7 +259,7 @@ __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, c
     const float dy[2] = { d1(y, c.cy[0]), d1(y, c.cy[1]) };
     const float dx[2] = { d1(x, c.cx[0]), d1(x, c.cx[1]) };
     const bool binary = (m.y == 0.0f) || (m.x == 0.0f);            // {0,1} masks: one polarity plane is read
-    const float2 *g0 = slot_base + ((m.x != 0.0f) ? 0 : g.plane);   // phase 0, plane of the (first) active polarity
+    const float2 *g0 = slot_base + ((m.x != 0.0f) ? 0 : g.plane);   // [pol][H][Wp] planes; the (first) active polarity
     const float m0 = (m.x != 0.0f) ? m.x : m.y;
 #pragma unroll
     for (int ky = 0; ky < 2; ++ky)
@@ -249,17 +277,26 @@ __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, c
 
 // dL/dmap of one bilinear flow sample: two 16-byte reductions (one per tap row)
 // into the dual-phase packed gradient map; c_k = dt * w_k, value = c_k * (g_x, g_y).
+template <bool DET>
 __device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const ImgGeom &g, const Taps &tp, float dt, float gpy, float gpx) {
     if (tp.x0 < -1) return;                                         // sample outside the map: all taps invalid
     const int phase = tp.x0 & 1;
     const int col = tp.x0 + phase;
-    float2 *base = gmap_phase0 + (long)phase * g.plane;
 #pragma unroll
     for (int ky = 0; ky < 2; ++ky) {
         if (!(tp.ok[2 * ky] || tp.ok[2 * ky + 1])) continue;
         const float cl = tp.ok[2 * ky] ? dt * tp.w[2 * ky] : 0.0f;
         const float cr = tp.ok[2 * ky + 1] ? dt * tp.w[2 * ky + 1] : 0.0f;
-        red_add_v4(base + (long)(tp.y0 + ky) * g.Wp + col, cl * gpx, cl * gpy, cr * gpx, cr * gpy);
+        const long off = (long)phase * g.plane + (long)(tp.y0 + ky) * g.Wp + col;
+        if (!DET) {
+            red_add_v4(gmap_phase0 + off, cl * gpx, cl * gpy, cr * gpx, cr * gpy);
+        } else {
+            long long *dst = reinterpret_cast<long long *>(gmap_phase0) + off * 2;
+            const float v[4] = { cl * gpx, cl * gpy, cr * gpx, cr * gpy };
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (v[k] != 0.0f) red_add_i64(dst + k, to_fix(v[k]));
+        }
     }
 }
 

@@ -33,16 +33,23 @@ __global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_consta
 }
 
 // dual-phase packed gradient [F][P][B][phase][H][Wp] float2 -> [P][F][B][2][H][W]
+template <bool DET>
 __global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__restrict__ packed, float *__restrict__ out, int F, int P, int B,
                                                                int W, long HW, ImgGeom g) {
     const int fp = blockIdx.z, b = blockIdx.y;
     const int f = fp / P, t = fp % P;
-    const float2 *src = packed + (((long)f * P + t) * B + b) * 2 * g.plane;
+    const float2 *src = packed + (((long)f * P + t) * B + b) * (DET ? 4 : 2) * g.plane;
     float *ox = out + ((((long)t * F + f) * B + b) * 2) * HW, *oy = ox + HW;
     for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < HW; i += (long)gridDim.x * kThreads) {
         const long o = (i / W) * g.Wp + (i % W);
-        const float2 a = src[o], c = src[g.plane + o + 1];
-        ox[i] = a.x + c.x; oy[i] = a.y + c.y;
+        if (!DET) {
+            const float2 a = src[o], c = src[g.plane + o + 1];
+            ox[i] = a.x + c.x; oy[i] = a.y + c.y;
+        } else {
+            const longlong2 *q = reinterpret_cast<const longlong2 *>(src);
+            const longlong2 a = q[o], c = q[g.plane + o + 1];
+            ox[i] = from_fix(a.x + c.x); oy[i] = from_fix(a.y + c.y);
+        }
     }
 }
 
@@ -73,14 +80,15 @@ extern "C" int tef_pack_flow(const void *const *flow_maps_host, int F, int t, in
     return (int)cudaGetLastError();
 }
 
-extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, void *stream) {
+extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream) {
     if (!packed || !out || F < 1 || P < 1 || B < 1) return TEF_EINVAL;
     const long HW = (long)H * W;
     int bx = (int)((HW + kThreads - 1) / kThreads);
     if (bx > 148 * 4) bx = 148 * 4;
     ProfScope ps(K_UNPACK_GRAD, (cudaStream_t)stream);
     ImgGeom g; g.Wp = (W + 3) & ~1; g.plane = (long)H * g.Wp;
-    unpack_grad_kernel<<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
+    if (deterministic) unpack_grad_kernel<true><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
+    else unpack_grad_kernel<false><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
     return (int)cudaGetLastError();
 }
 

@@ -103,6 +103,7 @@ __device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
     return t >= lo_e && t < hi_e;
 }
 
+template <bool DET>
 __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
     int t, b, row, set; float4 e; float2 m;
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
         p.alivebuf[(long)f * p.rows_grad + row] = alive;
     }
 
-    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
+    const long slot_stride = (DET ? 8 : 4) * p.ig.plane;          // float2 elements per slot (int64 pairs in deterministic mode)
+    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
     for (int s = 0; s < p.sc.S; ++s) {
         Win w;
         if (!window_of(p, s, t, alive, w)) continue;
@@ -130,18 +132,19 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
             if (!p.border && !((alive >> tr) & 1u)) continue;
             const float nts = 1.0f - div_const(fabsf((float)tr - e.x), fdelta, rdelta);   // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
-            splat<true>(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m);
+            splat<true, DET>(img_fb + (long)(w.slot0 + tr) * slot_stride, p.res, p.ig, q.x, q.y, nts, m);
         }
     }
 }
 
 // one reverse chain step: reduce dL/dmap, return dL/d(source position)
+template <bool DET>
 __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
                                          float sx, float dt, float gpy, float gpx, float &cy_, float &cx_) {
     Taps tp;
     if (inside(sy, sx, r)) sample_flow_inside<true>(map, r, sy, sx, &tp);
     else sample_flow<true>(map, r, sy, sx, &tp);
-    taps_red(gmap, g, tp, dt, gpy, gpx);
+    taps_red<DET>(gmap, g, tp, dt, gpy, gpx);
     const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
     const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
     const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
@@ -153,13 +156,15 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
 // One thread per gradient-carrying event.  Chain positions come from the forward kernel's posbuf
 // (coalesced loads); per node: gather the gradient images at the corners, add what flows back from the
 // next node, reduce into the packed flow-gradient map and step towards the event's own window.
+template <bool DET>
 __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
-    float2 *gflow_f = p.gflow + (long)f * p.P * p.B * 2 * p.ig.plane;
+    const long gmap_sz = (DET ? 4 : 2) * p.ig.plane;               // float2 elements per (pass, sample) gradient map
+    float2 *gflow_f = p.gflow + (long)f * p.P * p.B * gmap_sz;
     const float ts = e.x, y0 = e.y, x0 = e.z;
     const uint32_t alive = p.alivebuf[(long)f * p.rows_grad + row];
     const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
@@ -176,7 +181,9 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         hi_node = max(hi_node, min(w.high_tref - 1, t + w.delta));
     }
     if (!has) return;
-    const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
+    // gradient images: [pol][H][Wp] float2 per slot -- the phase-0 planes of img, or gimg in deterministic mode
+    const long gslot = (DET ? 2 : 4) * p.ig.plane;
+    const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         for (int s = 0; s < p.sc.S; ++s) {
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             if (!feeds(w, tr, t)) continue;
             const float fdelta = (float)w.delta;
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
-            iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * 4 * p.ig.plane, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+            iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
 
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : 1.0f;
                 const long mo = (long)(tr - 1) * p.B + b;
-                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(flow_f + mo * HW, gflow_f + mo * gmap_sz, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : -1.0f;
                 const long mo = (long)tr * p.B + b;
-                step_bwd(flow_f + mo * HW, gflow_f + mo * 2 * p.ig.plane, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(flow_f + mo * HW, gflow_f + mo * gmap_sz, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
@@ -250,10 +257,16 @@ static size_t chain_smem(const CmParams &p) { return sizeof(float2) * (size_t)(p
 static int launch_fwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(iter_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads)); attr = true; }
+        if (!attr) {
+            const int mx = (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads);
+            cudaFuncSetAttribute(iter_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(iter_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            attr = true;
+        }
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_FWD, st);
-        iter_fwd_kernel<<<grid, kThreads, chain_smem(p), st>>>(p);
+        if (p.det) iter_fwd_kernel<true><<<grid, kThreads, chain_smem(p), st>>>(p);
+        else iter_fwd_kernel<false><<<grid, kThreads, chain_smem(p), st>>>(p);
     }
     return (int)cudaGetLastError();
 }
@@ -261,7 +274,8 @@ static int launch_bwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_BWD, st);
-        iter_bwd_kernel<<<grid, kThreads, 0, st>>>(p);
+        if (p.det) iter_bwd_kernel<true><<<grid, kThreads, 0, st>>>(p);
+        else iter_bwd_kernel<false><<<grid, kThreads, 0, st>>>(p);
     }
     return (int)cudaGetLastError();
 }
@@ -273,7 +287,7 @@ extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
     const long nimg = (long)p.F * p.B * p.nslots;
-    cudaMemsetAsync(p.img, 0, sizeof(float2) * nimg * 4 * p.ig.plane, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * nimg * (p.det ? 8 : 4) * p.ig.plane, st);
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     rc = launch_fwd(p, st);
@@ -289,7 +303,8 @@ extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
     if (p.rows_grad > 0 && (!p.posbuf || !p.alivebuf)) return TEF_EINVAL;
     grad_segments_only(p);
-    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * 2 * p.ig.plane, st);
+    if (p.det && !p.gimg) return TEF_EINVAL;
+    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * (p.det ? 4 : 2) * p.ig.plane, st);
     rc = tef_grad_images(p, st);
     if (rc) return rc;
     rc = launch_bwd(p, st);

@@ -21,6 +21,7 @@ __device__ __forceinline__ bool linear_ends(const CmParams &p, float lo, float h
     return inside(fw.x, fw.y, p.res) && inside(bw.x, bw.y, p.res);
 }
 
+template <bool DET>
 __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
@@ -28,7 +29,8 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
     const long HW = (long)p.H * p.W;
     const float2 vxy = sample_flow<false>(p.flow + (((long)f * p.P + t) * p.B + b) * HW, p.res, e.y, e.z, nullptr);
     const float2 v = make_float2(vxy.y, vxy.x);                        // (y, x), utils/iwe.py:38
-    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
+    const long slot_stride = (DET ? 8 : 4) * p.ig.plane;
+    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
     for (int s = 0; s < p.sc.S; ++s) {
         const int L = p.sc.L[s];
         if (t >= (L << s)) continue;
@@ -39,15 +41,16 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;    // iwe_formatting(.., high_pass, scale) (:345-351)
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
         if (p.border) {      // both ends passed purge_unfeasible: in-image fast path
-            splat<true>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
-            splat<true>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
+            splat<true, DET>(img_fb + (long)slot * slot_stride, p.res, p.ig, fw.x, fw.y, nf, m);
+            splat<true, DET>(img_fb + (long)(slot + 1) * slot_stride, p.res, p.ig, bw.x, bw.y, nb, m);
         } else {
-            splat<false>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m);
-            splat<false>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m);
+            splat<false, DET>(img_fb + (long)slot * slot_stride, p.res, p.ig, fw.x, fw.y, nf, m);
+            splat<false, DET>(img_fb + (long)(slot + 1) * slot_stride, p.res, p.ig, bw.x, bw.y, nb, m);
         }
     }
 }
 
+template <bool DET>
 __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
@@ -57,7 +60,8 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
     Taps tp;
     const float2 vxy = sample_flow<true>(p.flow + mo, p.res, e.y, e.z, &tp);
     const float2 v = make_float2(vxy.y, vxy.x);
-    const float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * 4 * p.ig.plane;
+    const long gslot = (DET ? 2 : 4) * p.ig.plane;
+    const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
     float gvy = 0.f, gvx = 0.f;
     for (int s = 0; s < p.sc.S; ++s) {
         const int L = p.sc.L[s];
@@ -69,14 +73,14 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
         const float nf = 1.0f - fabsf((float)hi - e.x) / (float)L;
         const float nb = 1.0f - fabsf((float)lo - e.x) / (float)L;
         float gy = 0.f, gx = 0.f;
-        iwe_grad<false>(img_fb + (long)slot * 4 * p.ig.plane, p.res, p.ig, fw.x, fw.y, nf, m, gy, gx);
+        iwe_grad<false>(img_fb + (long)slot * gslot, p.res, p.ig, fw.x, fw.y, nf, m, gy, gx);
         gvy += dth * gy; gvx += dth * gx;
         gy = 0.f; gx = 0.f;
-        iwe_grad<false>(img_fb + (long)(slot + 1) * 4 * p.ig.plane, p.res, p.ig, bw.x, bw.y, nb, m, gy, gx);
+        iwe_grad<false>(img_fb + (long)(slot + 1) * gslot, p.res, p.ig, bw.x, bw.y, nb, m, gy, gx);
         gvy += dtl * gy; gvx += dtl * gx;
     }
     if (gvy == 0.f && gvx == 0.f) return;
-    taps_red(p.gflow + (((long)f * p.P + t) * p.B + b) * 2 * p.ig.plane, p.ig, tp, 1.0f, gvy, gvx);
+    taps_red<DET>(p.gflow + (((long)f * p.P + t) * p.B + b) * (DET ? 4 : 2) * p.ig.plane, p.ig, tp, 1.0f, gvy, gvx);
 }
 
 }  // namespace tef
@@ -93,12 +97,13 @@ extern "C" int tef_linear_forward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 1, p);
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
-    cudaMemsetAsync(p.img, 0, sizeof(float2) * (long)p.F * p.B * p.nslots * 4 * p.ig.plane, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * (long)p.F * p.B * p.nslots * (p.det ? 8 : 4) * p.ig.plane, st);
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         ProfScope ps(K_LIN_FWD, st);
-        linear_fwd_kernel<<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        if (p.det) linear_fwd_kernel<true><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        else linear_fwd_kernel<false><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
     }
     rc = (int)cudaGetLastError();
     if (rc) return rc;
@@ -112,12 +117,14 @@ extern "C" int tef_linear_backward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
     grad_segments_only(p);
-    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * 2 * p.ig.plane, st);
+    if (p.det && !p.gimg) return TEF_EINVAL;
+    cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * (p.det ? 4 : 2) * p.ig.plane, st);
     rc = tef_grad_images(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         ProfScope ps(K_LIN_BWD, st);
-        linear_bwd_kernel<<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        if (p.det) linear_bwd_kernel<true><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        else linear_bwd_kernel<false><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
     }
     return (int)cudaGetLastError();
 }

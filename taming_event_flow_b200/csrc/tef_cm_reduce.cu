@@ -16,23 +16,31 @@ __device__ __forceinline__ int scale_of_slot(const ScaleTable &sc, int q) {
 }
 
 // sum of the two phases of one pixel: (count, time-weighted count) of one polarity
+template <bool DET>
 __device__ __forceinline__ float2 pixel_sum(const float2 *__restrict__ slot_base, const ImgGeom &g, int pol, long o) {
-    const float2 a = slot_base[(long)pol * g.plane + o];                 // phase 0: column x
-    const float2 b = slot_base[(long)(2 + pol) * g.plane + o + 1];       // phase 1: column x + 1
-    return make_float2(a.x + b.x, a.y + b.y);
+    if (!DET) {
+        const float2 a = slot_base[(long)pol * g.plane + o];                 // phase 0: column x
+        const float2 b = slot_base[(long)(2 + pol) * g.plane + o + 1];       // phase 1: column x + 1
+        return make_float2(a.x + b.x, a.y + b.y);
+    }
+    const longlong2 *q = reinterpret_cast<const longlong2 *>(slot_base);
+    const longlong2 a = q[(long)pol * g.plane + o], b = q[(long)(2 + pol) * g.plane + o + 1];
+    return make_float2(from_fix(a.x + b.x), from_fix(a.y + b.y));            // exact integer sum, one rounding
 }
 
-__global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__restrict__ img, double *__restrict__ acc_sum,
-                                                              int *__restrict__ acc_nnz, int W, long HW, ImgGeom g) {
+// per-CTA partial sums in a fixed slot (no atomics): the final per-image sum has a fixed order in both modes
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__restrict__ img, double *__restrict__ part_sum,
+                                                              int *__restrict__ part_nnz, int W, long HW, ImgGeom g) {
     const long image = blockIdx.y;
-    const float2 *im = img + image * 4 * g.plane;
+    const float2 *im = img + image * (DET ? 8 : 4) * g.plane;
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     double acc = 0.0;
     int cnt = 0;
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
         const long o = (i / W) * g.Wp + (i % W);
-        const float2 vp = pixel_sum(im, g, 0, o), vn = pixel_sum(im, g, 1, o);
+        const float2 vp = pixel_sum<DET>(im, g, 0, o), vn = pixel_sum<DET>(im, g, 1, o);
         const float ap = vp.y / (vp.x + 1e-9f);       // loss/flow.py:727
         const float an = vn.y / (vn.x + 1e-9f);
         acc += (double)(ap * ap) + (double)(an * an); // :123
@@ -51,8 +59,8 @@ __global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__re
     if (threadIdx.x == 0) {
         double a = 0.0; int c = 0;
         for (int k = 0; k < kThreads / 32; ++k) { a += s_acc[k]; c += s_cnt[k]; }
-        atomicAdd(acc_sum + image, a);
-        atomicAdd(acc_nnz + image, c);
+        part_sum[image * gridDim.x + blockIdx.x] = a;
+        part_nnz[image * gridDim.x + blockIdx.x] = c;
     }
 }
 
@@ -63,11 +71,14 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
     for (int i = threadIdx.x; i < nimg; i += kThreads) {
         const int q = i % p.nslots;
         const int s = scale_of_slot(p.sc, q);
-        const float den = p.loss_scaling ? ((float)p.acc_nnz[i] + 1e-9f) : 1.0f;
+        double sum = 0.0; int nnz = 0;
+        for (int c = 0; c < p.nchunks; ++c) { sum += p.acc_sum[(long)i * p.nchunks + c]; nnz += p.acc_nnz[(long)i * p.nchunks + c]; }
+        const float den = p.loss_scaling ? ((float)nnz + 1e-9f) : 1.0f;
         p.den[i] = den;
         const double div_a = p.linear ? 2.0 : (double)(2 * p.sc.delta[s] + 1);
-        acc += p.acc_sum[i] / (double)den / (double)(1 << s) / div_a / (double)p.sc.S / (double)p.F;
+        acc += sum / (double)den / (double)(1 << s) / div_a / (double)p.sc.S / (double)p.F;
     }
+    // fixed-order tree: shuffle reduction inside each warp, then warps in order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     __shared__ double s_acc[kThreads / 32];
@@ -82,24 +93,26 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
 
 // in place: (cnt, ts) -> (dL/dcnt, dL/dts) per polarity, in autograd's operation order
 // (pow: grad*(2*A); div: grad/D and -grad*((T/D)/D)), see oracle/cm_oracle_impl.h phase 3.
+template <bool DET>
 __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constant__ CmParams p, long HW) {
     const long image = blockIdx.y;
     const int q = (int)(image % p.nslots);
     const int s = scale_of_slot(p.sc, q);
     const float div_a = p.linear ? 2.0f : (float)(2 * p.sc.delta[s] + 1);
     const float cf = upstream(__ldg(p.grad_out), p.F, p.sc.S, div_a, s) / p.den[image];
-    float2 *im = p.img + image * 4 * p.ig.plane;
+    float2 *im = p.img + image * (DET ? 8 : 4) * p.ig.plane;
+    float2 *out = DET ? p.gimg + image * 2 * p.ig.plane : im;     // [pol][H][Wp]; in place (phase-0 planes) unless deterministic
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
         const long o = (i / p.W) * p.ig.Wp + (i % p.W);
 #pragma unroll
         for (int pol = 0; pol < 2; ++pol) {
-            const float2 v = pixel_sum(im, p.ig, pol, o);
+            const float2 v = pixel_sum<DET>(im, p.ig, pol, o);
             const float d = v.x + 1e-9f;
             const float a = v.y / d;
             const float ga = cf * (2.0f * a);
-            im[(long)pol * p.ig.plane + o] = make_float2(-(ga * (a / d)), ga / d);    // (dL/dcount, dL/dtime-weighted), phase-0 plane
+            out[(long)pol * p.ig.plane + o] = make_float2(-(ga * (a / d)), ga / d);    // (dL/dcount, dL/dtime-weighted)
         }
     }
 }
@@ -111,10 +124,12 @@ using namespace tef;
 int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st) {
     const long HW = (long)p.H * p.W;
     const int nimg = p.F * p.B * p.nslots;
-    cudaMemsetAsync(p.acc_sum, 0, sizeof(double) * nimg, st);
-    cudaMemsetAsync(p.acc_nnz, 0, sizeof(int) * nimg, st);
-    dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), nimg);
-    { ProfScope ps(K_IWE_REDUCE, st); iwe_reduce_kernel<<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig); }
+    dim3 grid((unsigned)p.nchunks, nimg);
+    {
+        ProfScope ps(K_IWE_REDUCE, st);
+        if (p.det) iwe_reduce_kernel<true><<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig);
+        else iwe_reduce_kernel<false><<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig);
+    }
     { ProfScope ps(K_FINALIZE, st); finalize_kernel<<<1, kThreads, 0, st>>>(p); }
     return (int)cudaGetLastError();
 }
@@ -122,9 +137,10 @@ int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st) {
 int tef_grad_images(const CmParams &p, cudaStream_t st) {
     const long HW = (long)p.H * p.W;
     const int nimg = p.F * p.B * p.nslots;
-    dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), nimg);
+    dim3 grid((unsigned)p.nchunks, nimg);
     ProfScope ps(K_IWE_GRAD, st);
-    iwe_grad_kernel<<<grid, kThreads, 0, st>>>(p, HW);
+    if (p.det) iwe_grad_kernel<true><<<grid, kThreads, 0, st>>>(p, HW);
+    else iwe_grad_kernel<false><<<grid, kThreads, 0, st>>>(p, HW);
     return (int)cudaGetLastError();
 }
 
@@ -143,13 +159,16 @@ extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     long r = 0;
     for (int s = 0; s < p.seg.nseg; ++s) r += (long)p.B * p.seg.n[s];
     out[0] = p.nslots;
-    out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2;     // floats in img
-    out[2] = (long)p.F * p.P * p.B * 2 * p.ig.plane * 2;          // floats in gflow
+    const long wide = p.det ? 2 : 1;                              // deterministic mode: int64 instead of float
+    out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 * wide;   // floats in img
+    out[2] = (long)p.F * p.P * p.B * 2 * p.ig.plane * 2 * wide;        // floats in gflow
     out[3] = p.sort.nbins + 1;                                    // ints in sort_bins
     out[4] = p.sort.nbins / 2048 + 2;                             // ints in sort_sums
     out[5] = r;                                                   // rows of sorted_ev / sorted_mk
     out[6] = p.rows_grad;                                         // gradient-carrying rows
     out[7] = linear ? 0 : (long)p.F * (p.P + 1) * p.rows_grad * 2; // floats in posbuf (alivebuf: F * rows_grad u64)
     out[8] = p.ig.Wp;
+    out[9] = p.nchunks;                                           // partial sums per image: acc_sum / acc_nnz hold F*B*slots*nchunks entries
+    out[10] = p.det ? (long)p.F * p.B * p.nslots * 2 * p.ig.plane * 2 : 0;   // floats in gimg (deterministic mode)
     return 0;
 }

@@ -212,9 +212,9 @@ class BaseEventWarping(torch.nn.Module):
     def _forward_kernels(self, w):
         F, B, H, W = w.shape
         d = self._desc(w)
-        sz = (ctypes.c_long * 9)()
+        sz = (ctypes.c_long * 11)()
         check(lib().tef_cm_sizes(ctypes.byref(d), int(self._linear), sz), "tef_cm_sizes")
-        nslots, n_img, _, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp = (int(v) for v in sz)
+        nslots, n_img, w.n_gflow, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp, nchunks, n_gimg = (int(v) for v in sz)
         dev = w.packed.device
         i32, f32 = torch.int32, torch.float32
         if w.ws is None:
@@ -223,8 +223,9 @@ class BaseEventWarping(torch.nn.Module):
         w.sort = (g("bins", (n_bins,), i32, dev), g("sums", (n_sums,), i32, dev), g("sorted_ev", (max(rows, 1), 8), f32, dev),
                   g("posbuf", (max(n_pos, 1),), f32, dev), g("alive", (max(F * rows_grad, 1),), i32, dev))
         w.img = g("img", (n_img,), f32, dev)
-        w.acc_sum = g("acc_sum", (F, B, nslots), torch.float64, dev)
-        w.acc_nnz = g("acc_nnz", (F, B, nslots), i32, dev)
+        w.gimg = g("gimg", (max(n_gimg, 1),), f32, dev)
+        w.acc_sum = g("acc_sum", (F, B, nslots, nchunks), torch.float64, dev)
+        w.acc_nnz = g("acc_nnz", (F, B, nslots, nchunks), i32, dev)
         w.den = g("den", (F, B, nslots), f32, dev)
         w.nslots = nslots
         loss = torch.empty((1,), dtype=f32, device=dev)
@@ -238,7 +239,7 @@ class BaseEventWarping(torch.nn.Module):
     @staticmethod
     def _fill_workspace(d, w):
         d.sort_bins, d.sort_sums, d.sorted_ev, d.posbuf, d.alivebuf = (x.data_ptr() for x in w.sort)
-        d.img, d.den = w.img.data_ptr(), w.den.data_ptr()
+        d.img, d.den, d.gimg = w.img.data_ptr(), w.den.data_ptr(), w.gimg.data_ptr()
 
     def _backward_kernels(self, w, gout):
         if w.consumed:
@@ -247,14 +248,14 @@ class BaseEventWarping(torch.nn.Module):
         P = self._max_passes()
         d = self._desc(w)
         dev = w.packed.device
-        gpacked = w.ws.get("gpacked", (F, P, B, 2, H, w.Wp, 2), torch.float32, dev)
+        gpacked = w.ws.get("gpacked", (w.n_gflow,), torch.float32, dev)
         grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)     # handed to autograd: not pooled
         g = gout.detach().float().contiguous().reshape(1)
         self._fill_workspace(d, w)
         d.gflow, d.grad_out = gpacked.data_ptr(), g.data_ptr()
         fn = lib().tef_linear_backward if self._linear else lib().tef_iterative_backward
         check(fn(ctypes.byref(d), stream()), "tef_linear_backward" if self._linear else "tef_iterative_backward")
-        check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, stream()), "tef_unpack_flow_grad")
+        check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, int(self.deterministic), stream()), "tef_unpack_flow_grad")
         w.consumed = True
         w.release()                # stream order makes reuse by the next window safe
         return grads
@@ -266,8 +267,12 @@ class BaseEventWarping(torch.nn.Module):
         if w.img is None or w.consumed:
             raise RuntimeError("images() is only available between forward() and backward()")
         F, B, H, W = w.shape
-        v = w.img.view(F, B, w.nslots, 2, 2, H, w.Wp, 2)              # [.., phase, pol, H, Wp, (count, tw)]
-        s = v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]
+        if self.deterministic:                                        # int64 fixed point, 2^-40
+            v = w.img.view(torch.int64).view(F, B, w.nslots, 2, 2, H, w.Wp, 2)
+            s = ((v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]).double() * 2.0 ** -40).float()
+        else:
+            v = w.img.view(F, B, w.nslots, 2, 2, H, w.Wp, 2)          # [.., phase, pol, H, Wp, (count, tw)]
+            s = v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]
         return torch.stack([s[:, :, :, 0, :, :, 0], s[:, :, :, 1, :, :, 0], s[:, :, :, 0, :, :, 1], s[:, :, :, 1, :, :, 1]], dim=3)
 
     # ---------------------------------------------------------------- forward

@@ -230,3 +230,34 @@ def test_events_to_channels_batched_matches_per_sample():
         n = int((ev[b, :, 3] != 0).sum())
         ref = events_to_channels(ev[b, :n, 2].cuda(), ev[b, :n, 1].cuda(), ev[b, :n, 3].cuda(), (H, W))
         assert torch.equal(out[b], ref)
+
+
+@pytest.mark.parametrize("kind", ["iterative", "linear"])
+def test_deterministic_mode_is_order_independent_and_bit_reproducible(kind):
+    """config["loss"]["deterministic"] = True: 64-bit fixed-point integer reductions.  Permuting the events of every window
+    (and re-running) gives bit-identical images, loss and gradients; the results stay within 1e-5 of the oracle."""
+    B, P, N, Nd, H, W, F = 2, 6, 3000, 1000, 64, 80, 2
+    seq = syn.make_sequence(17, B, P, N, Nd, H, W, F, 3.0)
+    cfg = syn.loss_config(H, W, B, P)
+    cfg["loss"]["deterministic"] = True
+    g = torch.Generator().manual_seed(99)
+    runs = []
+    for rep in range(3):
+        ev, mk, dev, dmk = [], [], [], []
+        for t in range(P):
+            pe = torch.randperm(N, generator=g) if rep else torch.arange(N)
+            pd = torch.randperm(Nd, generator=g) if rep else torch.arange(Nd)
+            ev.append(seq["events"][t][:, pe]); mk.append(seq["masks"][t][:, pe])
+            dev.append(seq["d_events"][t][:, pd]); dmk.append(seq["d_masks"][t][:, pd])
+        runs.append(_run_gpu(kind, copy.deepcopy(cfg), seq["flows"], ev, mk, dev, dmk))
+    for r in runs[1:]:
+        assert r["loss"] == runs[0]["loss"]
+        assert np.array_equal(r["iwe"], runs[0]["iwe"])
+        assert np.array_equal(r["gflow"], runs[0]["gflow"])
+    oc = orc.make_cfg(B, H, W, P, F)
+    fn = orc.iterative if kind == "iterative" else orc.linear
+    o = fn(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], np.float32, want_grad=True, want_iwe=True)
+    assert abs(runs[0]["loss"] - o["loss"]) <= TOL * abs(o["loss"])
+    assert rel_err(runs[0]["iwe"], o["iwe"])[0] < TOL
+    assert np.array_equal(runs[0]["iwe"] != 0, o["iwe"] != 0)
+    assert rel_err(runs[0]["gflow"], o["gflow"])[0] < TOL
