@@ -92,6 +92,22 @@ int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B,
 /* backward counterpart: packed gradient -> [P][F][B][2][H][W] */
 int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream);
 
+/* The whole of Iterative.update / Linear.update in one call (two launches): tef_pack_flow for the F maps of pass `t`
+   plus tef_stage_events for the gradient-carrying set [0] and the detached set [1]. */
+typedef struct tef_update_desc {
+    int F, t, P, B, H, W;
+    const void *flow_maps[TEF_MAX_FLOWS];  /* [B][2][H][W] each                                   */
+    void *packed;                          /* [F][P][B][H][W] float2                              */
+    void *events[2];                       /* caller's [B][n][4]; ts += pass_index in place       */
+    const void *masks[2];                  /* [B][n][2]                                           */
+    void *ev_out[2];                       /* staged rows float4                                  */
+    void *mk_out[2];                       /* staged masks float2                                 */
+    long rows[2];                          /* B * n                                               */
+    float pass_index[2];
+    const float *ts_override[2];           /* round_ts device scalars or NULL                     */
+} tef_update_desc;
+int tef_update_pass(const tef_update_desc *u, void *stream);
+
 /* Iterative.forward (loss/flow.py:588-746) and its analytic backward */
 int tef_iterative_forward(const tef_cm_desc *d, void *stream);
 int tef_iterative_backward(const tef_cm_desc *d, void *stream);

@@ -55,6 +55,24 @@ class CmDesc(ctypes.Structure):
     )
 
 
+class UpdateDesc(ctypes.Structure):
+    """Mirror of ``tef_update_desc``."""
+    _fields_ = (
+        [(k, ctypes.c_int) for k in ("F", "t", "P", "B", "H", "W")]
+        + [
+            ("flow_maps", ctypes.c_void_p * MAX_FLOWS),
+            ("packed", ctypes.c_void_p),
+            ("events", ctypes.c_void_p * 2),
+            ("masks", ctypes.c_void_p * 2),
+            ("ev_out", ctypes.c_void_p * 2),
+            ("mk_out", ctypes.c_void_p * 2),
+            ("rows", ctypes.c_long * 2),
+            ("pass_index", ctypes.c_float * 2),
+            ("ts_override", ctypes.c_void_p * 2),
+        ]
+    )
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

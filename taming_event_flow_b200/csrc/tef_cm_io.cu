@@ -20,6 +20,23 @@ __global__ void __launch_bounds__(kThreads) stage_events_kernel(float4 *__restri
     mk_out[i] = mk_in[i];
 }
 
+// both event sets of one pass in one launch: CTAs [0, nb0) stage set 0, the rest set 1
+struct StageTwo {
+    float4 *ev_io[2]; const float2 *mk_in[2]; float4 *ev_out[2]; float2 *mk_out[2];
+    long rows[2]; float pass_index[2]; const float *ts_override[2]; int nb0;
+};
+__global__ void __launch_bounds__(kThreads) stage_two_kernel(const __grid_constant__ StageTwo s) {
+    const int k = blockIdx.x >= s.nb0 ? 1 : 0;
+    const long i = (long)(blockIdx.x - (k ? s.nb0 : 0)) * kThreads + threadIdx.x;
+    if (i >= s.rows[k]) return;
+    float4 e = s.ev_io[k][i];
+    e.x = e.x + s.pass_index[k];
+    s.ev_io[k][i] = e;
+    if (s.ts_override[k]) e.x = __ldg(s.ts_override[k]);
+    s.ev_out[k][i] = e;
+    s.mk_out[k][i] = s.mk_in[k][i];
+}
+
 struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
 
 // [B][2][H][W] planar (ch0 = x, ch1 = y) -> float2 interleaved [B][H][W]
@@ -89,6 +106,29 @@ extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P,
     ImgGeom g; g.Wp = (W + 3) & ~1; g.plane = (long)H * g.Wp;
     if (deterministic) unpack_grad_kernel<true><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
     else unpack_grad_kernel<false><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_update_pass(const tef_update_desc *u, void *stream) {
+    if (!u) return TEF_EINVAL;
+    if (u->F > 0) {
+        int rc = tef_pack_flow(u->flow_maps, u->F, u->t, u->P, u->B, u->H, u->W, u->packed, stream);
+        if (rc) return rc;
+    }
+    StageTwo s;
+    for (int k = 0; k < 2; ++k) {
+        if (u->rows[k] < 0) return TEF_EINVAL;
+        if (u->rows[k] > 0 && (!u->events[k] || !u->masks[k] || !u->ev_out[k] || !u->mk_out[k])) return TEF_EINVAL;
+        s.ev_io[k] = (float4 *)u->events[k]; s.mk_in[k] = (const float2 *)u->masks[k];
+        s.ev_out[k] = (float4 *)u->ev_out[k]; s.mk_out[k] = (float2 *)u->mk_out[k];
+        s.rows[k] = u->rows[k]; s.pass_index[k] = u->pass_index[k]; s.ts_override[k] = u->ts_override[k];
+    }
+    s.nb0 = (int)((u->rows[0] + kThreads - 1) / kThreads);
+    const int nb = s.nb0 + (int)((u->rows[1] + kThreads - 1) / kThreads);
+    if (nb > 0) {
+        ProfScope ps(K_STAGE_EVENTS, (cudaStream_t)stream);
+        stage_two_kernel<<<nb, kThreads, 0, (cudaStream_t)stream>>>(s);
+    }
     return (int)cudaGetLastError();
 }
 

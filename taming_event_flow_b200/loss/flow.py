@@ -47,7 +47,7 @@ class _Window:
         self.ws = pool.pop() if pool else _Workspace()
         self.flows = []        # flows[t][f]: the caller's tensors (autograd leaves of the loss)
         self.packed = None     # [F,P,B,H,W,2]
-        self.ev = ([], [])     # staged events per pass, (grad set, detached set)
+        self.ev = ([], [])     # device addresses of the staged event rows per pass, (grad set, detached set)
         self.mk = ([], [])
         self.n = ([], [])
         self.sort = None       # (bins, sums, sorted_ev, sorted_mk), written by the forward kernels
@@ -111,6 +111,7 @@ class BaseEventWarping(torch.nn.Module):
         self._num_flows = None
         self._pool = []
         self._win = _Window(self._pool)
+        self._fn_update = lib().tef_update_pass
 
         # timescales for loss computation (loss/flow.py:42-44)
         self.passes_loss = [config["data"]["passes_loss"] // (2 ** s) for s in range(config["data"]["scales_loss"])]
@@ -133,62 +134,83 @@ class BaseEventWarping(torch.nn.Module):
 
     # ----------------------------------------------------------------- update
     def update_base(self, flow_list):
-        """Pack this pass' flow maps (upstream ``update_base``, loss/flow.py:46-66)."""
+        """Validate this pass' flow maps and make sure the window has its packed buffer (upstream ``update_base``,
+        loss/flow.py:46-66).  The packing itself happens in `_update_pass`, fused with the event staging."""
         w = self._win
         if w.ws is None:
             raise RuntimeError("update() after backward(): call reset() first (upstream resets after every loss, train_flow.py:136-137)")
         if self._num_flows is None:
             self._num_flows = len(flow_list)
-        if len(flow_list) != self._num_flows:
-            raise ValueError("flow_list has %d maps, expected %d" % (len(flow_list), self._num_flows))
-        require_cuda(*flow_list)
         F = self._num_flows
-        B, C, H, W = flow_list[0].shape
-        if C != 2 or [H, W] != list(self.res):
-            raise ValueError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(flow_list[0].shape)))
+        if len(flow_list) != F:
+            raise ValueError("flow_list has %d maps, expected %d" % (len(flow_list), F))
         if F > _lib.MAX_FLOWS:
             raise _lib.TefError("at most %d flow maps per pass" % _lib.MAX_FLOWS)
-        P = self._max_passes()
+        f0 = flow_list[0]
+        if not f0.is_cuda:
+            require_cuda(f0)
+        B, C, H, W = f0.shape
+        if C != 2 or H != self.res[0] or W != self.res[1]:
+            raise ValueError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(f0.shape)))
         if w.packed is None:
             w.shape = (F, B, H, W)
-            w.packed = w.ws.get("packed", (F, P, B, H, W, 2), torch.float32, flow_list[0].device)
+            w.packed = w.ws.get("packed", (F, self._max_passes(), B, H, W, 2), torch.float32, f0.device)
         w.flows.append(list(flow_list))
-        t = self._passes
-        if t < P:
-            srcs = [fl.detach().contiguous().float() for fl in flow_list]
-            arr = (ctypes.c_void_p * F)(*[s.data_ptr() for s in srcs])
-            check(lib().tef_pack_flow(arr, F, t, P, B, H, W, ptr(w.packed), stream()), "tef_pack_flow")
 
-    def _stage(self, k, events, mask):
-        """Event part of `update` (loss/flow.py:456-473): ts += passes in place, keep a staged copy."""
+    def _update_pass(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
+        """One `tef_update_pass` call: pack the F flow maps of this pass, add the pass index to the caller's timestamps in
+        place (loss/flow.py:457-458) and keep a staged copy of the event rows and masks of both sets (:459-473)."""
         w = self._win
-        require_cuda(events, mask)
-        B, N = events.shape[0], events.shape[1]
-        rows = B * N
-        override = None
-        direct = events.is_contiguous() and events.dtype == torch.float32
-        if self.config["loss"]["round_ts"]:
-            # event_ts[...] = event_ts.min() + 0.5 (:461-463); min() of an empty tensor raises, like upstream
-            override = (events[:, :, 0].min() + float(self._passes) + 0.5).float().reshape(1)
-        t = len(w.ev[k])
-        ev_out = w.ws.get(("ev", k, t), (B, N, 4), torch.float32, events.device)
-        mk_out = w.ws.get(("mk", k, t), (B, N, 2), torch.float32, events.device)
-        if rows > 0:
-            if direct:
-                src, pass_index = events, float(self._passes)
+        t = self._passes
+        F, B, H, W = w.shape
+        P = self._max_passes()
+        u = _lib.UpdateDesc()
+        u.F, u.t, u.P, u.B, u.H, u.W = F, min(t, P - 1), P, B, H, W
+        keep = []                      # temporaries must outlive the (asynchronous) launches only in stream order
+        for f, fl in enumerate(flow_list):
+            if not (fl.is_cuda and fl.is_contiguous() and fl.dtype == torch.float32):
+                require_cuda(fl)
+                fl = fl.detach().contiguous().float()
+                keep.append(fl)
+            u.flow_maps[f] = fl.data_ptr()
+        u.packed = w.packed.data_ptr()
+        round_ts = self.config["loss"]["round_ts"]
+        dev = w.packed.device
+        for k, (ev, mk) in enumerate(((event_list, pol_mask), (d_event_list, d_pol_mask))):
+            if not (ev.is_cuda and mk.is_cuda):
+                require_cuda(ev, mk)
+            Bk, N = ev.shape[0], ev.shape[1]
+            rows = Bk * N
+            buf = w.ws.get(("stage", k, t), (rows, 6), torch.float32, dev)
+            base = buf.data_ptr()
+            w.ev[k].append(base)
+            w.mk[k].append(base + rows * 16)
+            w.n[k].append(N)
+            u.rows[k] = rows
+            if round_ts:
+                # event_ts[...] = event_ts.min() + 0.5 (:461-463); min() of an empty tensor raises, like upstream
+                ov = (ev[:, :, 0].min() + float(t) + 0.5).float().reshape(1)
+                keep.append(ov)
+                u.ts_override[k] = ov.data_ptr()
+            if rows == 0:
+                continue
+            if ev.is_contiguous() and ev.dtype == torch.float32:
+                u.events[k], u.pass_index[k] = ev.data_ptr(), float(t)
             else:
-                events[:, :, 0:1] += self._passes
-                src, pass_index = events.contiguous().float(), 0.0
-            mk = mask.contiguous().float()
-            check(lib().tef_stage_events(ptr(src), ptr(mk), ptr(ev_out), ptr(mk_out), ctypes.c_long(rows),
-                                         ctypes.c_float(pass_index), ptr(override), stream()), "tef_stage_events")
-        w.ev[k].append(ev_out)
-        w.mk[k].append(mk_out)
-        w.n[k].append(N)
-
-    def _update_events(self, event_list, pol_mask, d_event_list, d_pol_mask):
-        self._stage(0, event_list, pol_mask)
-        self._stage(1, d_event_list, d_pol_mask)
+                ev[:, :, 0:1] += t
+                src = ev.contiguous().float()
+                keep.append(src)
+                u.events[k], u.pass_index[k] = src.data_ptr(), 0.0
+            if not (mk.is_contiguous() and mk.dtype == torch.float32):
+                mk = mk.contiguous().float()
+                keep.append(mk)
+            u.masks[k] = mk.data_ptr()
+            u.ev_out[k], u.mk_out[k] = base, base + rows * 16
+        if t >= P:
+            # passes beyond the loss window are not part of the loss (upstream never reads them); only the in-place
+            # timestamp update is observable, so stage into the scratch rows and skip the packing slot
+            u.F = 0
+        check(self._fn_update(ctypes.byref(u), stream()), "tef_update_pass")
 
     # ---------------------------------------------------------------- kernels
     def _desc(self, w):
@@ -203,8 +225,8 @@ class BaseEventWarping(torch.nn.Module):
         d.deterministic = int(self.deterministic)
         for k in range(2):
             for t in range(P):
-                d.ev[k][t] = w.ev[k][t].data_ptr()
-                d.mk[k][t] = w.mk[k][t].data_ptr()
+                d.ev[k][t] = w.ev[k][t]
+                d.mk[k][t] = w.mk[k][t]
                 d.n[k][t] = w.n[k][t]
         d.flow = w.packed.data_ptr()
         return d
@@ -349,7 +371,7 @@ class Iterative(BaseEventWarping):
         """Same contract as upstream ``Iterative.update`` (:443-476), including the in-place
         ``event_list[:, :, 0] += num_passes`` on the caller's tensors."""
         self.update_base(flow_list)
-        self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
+        self._update_pass(flow_list, event_list, pol_mask, d_event_list, d_pol_mask)
         self._passes += 1
 
     def forward(self):
@@ -371,7 +393,7 @@ class Linear(BaseEventWarping):
         """Same contract as upstream ``Linear.update`` (:233-288).  Upstream samples the per-event flow here; the
         kernels sample the same values from this pass' packed map inside `forward`."""
         self.update_base(flow_list)
-        self._update_events(event_list, pol_mask, d_event_list, d_pol_mask)
+        self._update_pass(flow_list, event_list, pol_mask, d_event_list, d_pol_mask)
         self._passes += 1
 
     def forward(self):
