@@ -53,11 +53,12 @@ typedef struct tef_cm_desc {
     const void *ev[2][TEF_MAX_PASSES];
     const void *mk[2][TEF_MAX_PASSES];
     int n[2][TEF_MAX_PASSES];
-    const void *flow;      /* packed flow maps, float2 (x, y): [F][P][B][H][W]         */
+    const void *flow;      /* packed flow maps, float2 (x, y), dual-phase and zero-padded: [F][P][B][phase][H+1][Wp]
+                              (written by tef_pack_flow / tef_update_pass; Wp = (W+3)&~1)  */
     void *gflow;           /* gradient of the packed maps, dual-phase: [F][P][B][phase][H][Wp] float2 (backward) */
     void *img;             /* accumulation images, float2 (count, time-weighted): [F][B][slots][phase][pol][H][Wp];
                               pixel x lives at column x of phase 0 plus column x+1 of phase 1 (see csrc/tef_cm_common.cuh);
-                              after backward the phase-0 planes hold (dL/dcount, dL/dtime-weighted)              */
+                              after backward the planes hold (dL/dcount, dL/dtime-weighted) in both phases       */
     double *acc_sum;       /* [F][B][slots][chunks] partial sums of squared normalised timestamps (fixed-order reduction) */
     int *acc_nnz;          /* [F][B][slots][chunks] partial counts of pixels with at least one event */
     float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
@@ -69,7 +70,7 @@ typedef struct tef_cm_desc {
     void *sorted_ev;       /* 32-byte records [rows]: (ts, y, x, sample index bits, mask+, mask-, 0, 0), tile-sorted */
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
     void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
-    void *gimg;            /* deterministic mode only: gradient images float2 [F][B][slots][pol][H][Wp] */
+    void *gimg;            /* deterministic mode only: gradient images float2 [F][B][slots][phase][pol][H][Wp] */
 } tef_cm_desc;
 
 /* buffer sizes for the events currently described by `d`; out[11] =
@@ -97,7 +98,7 @@ int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int
 typedef struct tef_update_desc {
     int F, t, P, B, H, W;
     const void *flow_maps[TEF_MAX_FLOWS];  /* [B][2][H][W] each                                   */
-    void *packed;                          /* [F][P][B][H][W] float2                              */
+    void *packed;                          /* [F][P][B][2][H+1][Wp] float2                        */
     void *events[2];                       /* caller's [B][n][4]; ts += pass_index in place       */
     const void *masks[2];                  /* [B][n][2]                                           */
     void *ev_out[2];                       /* staged rows float4                                  */

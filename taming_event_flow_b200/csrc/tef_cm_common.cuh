@@ -250,29 +250,36 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
 }
 
 // gradient of the loss w.r.t. the position at one reference time, through the bilinear splat weights
-// (SURVEY.md Appendix A.4); the gradient images (dL/dcount, dL/dtime-weighted) live in the phase-0 planes.
+// (SURVEY.md Appendix A.4).  The gradient images (dL/dcount, dL/dtime-weighted) are stored in both phases
+// ([phase][pol][H][Wp] float2), so each image row is one 16-byte gather of the (left, right) corner pair.
 template <bool INSIDE>
 __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts,
                                          float2 m, float &gy, float &gx) {
     Corners c;
     corners<INSIDE>(y, x, r, c);
+    if (!INSIDE && !(c.okx[0] || c.okx[1])) return;
+    const int xl = (INSIDE || c.okx[0]) ? (int)c.cx[0] : (int)c.cx[1] - 1;
+    const int phase = xl & 1;
+    const int col = xl + phase;
     const float dy[2] = { d1(y, c.cy[0]), d1(y, c.cy[1]) };
     const float dx[2] = { d1(x, c.cx[0]), d1(x, c.cx[1]) };
     const bool binary = (m.y == 0.0f) || (m.x == 0.0f);            // {0,1} masks: one polarity plane is read
-    const float2 *g0 = slot_base + ((m.x != 0.0f) ? 0 : g.plane);   // [pol][H][Wp] planes; the (first) active polarity
-    const float m0 = (m.x != 0.0f) ? m.x : m.y;
+    const int pol0 = (m.x != 0.0f) ? 0 : 1;
+    const float m0 = pol0 ? m.y : m.x;
+    const float2 *g0 = slot_base + (long)(phase * 2 + pol0) * g.plane;
 #pragma unroll
-    for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 2; ++kx) {
-            if (!(c.oky[ky] && c.okx[kx])) continue;
-            const int off = (int)c.cy[ky] * g.Wp + (int)c.cx[kx];
-            const float2 v = __ldg(g0 + off);
-            float gw = m0 * (v.x + nts * v.y);
-            if (!binary) { const float2 u = __ldg(slot_base + g.plane + off); gw = gw + m.y * (u.x + nts * u.y); }
-            gy += gw * dy[ky] * c.wx[kx];
-            gx += gw * c.wy[ky] * dx[kx];
+    for (int ky = 0; ky < 2; ++ky) {
+        if (!c.oky[ky]) continue;
+        const int off = (int)c.cy[ky] * g.Wp + col;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(g0 + off));
+        float gl = m0 * (v.x + nts * v.y), gr = m0 * (v.z + nts * v.w);
+        if (!binary) {
+            const float4 u = __ldg(reinterpret_cast<const float4 *>(slot_base + (long)(phase * 2 + 1) * g.plane + off));
+            gl = gl + m.y * (u.x + nts * u.y); gr = gr + m.y * (u.z + nts * u.w);
         }
+        if (c.okx[0]) { gy += gl * dy[ky] * c.wx[0]; gx += gl * c.wy[ky] * dx[0]; }
+        if (c.okx[1]) { gy += gr * dy[ky] * c.wx[1]; gx += gr * c.wy[ky] * dx[1]; }
+    }
 }
 
 // dL/dmap of one bilinear flow sample: two 16-byte reductions (one per tap row)

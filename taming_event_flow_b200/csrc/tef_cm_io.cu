@@ -39,17 +39,23 @@ __global__ void __launch_bounds__(kThreads) stage_two_kernel(const __grid_consta
 
 struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
 
-// [B][2][H][W] planar (ch0 = x, ch1 = y) -> float2 interleaved [B][H][W]
+// [B][2][H][W] planar (ch0 = x, ch1 = y) -> dual-phase float2 [B][phase][H+1][Wp] with zero padding (tef_device.cuh)
 __global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_constant__ FlowPtrs src, float2 *__restrict__ packed, int t, int P,
-                                                             int B, long HW) {
+                                                             int B, Res r) {
     const int f = blockIdx.z, b = blockIdx.y;
+    const long HW = (long)r.H * r.W;
     const float *sx = src.p[f] + (long)b * 2 * HW, *sy = sx + HW;
-    float2 *dst = packed + (((long)f * P + t) * B + b) * HW;
-    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < HW; i += (long)gridDim.x * kThreads)
-        dst[i] = make_float2(sx[i], sy[i]);
+    float2 *dst = packed + (((long)f * P + t) * B + b) * 2 * r.fplane;
+    const int n = 2 * r.fplane;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const int phase = i >= r.fplane;
+        const int q = i - phase * r.fplane;
+        const int y = q / r.Wp, x = q % r.Wp - phase;
+        const bool in = (y < r.H) && (x >= 0) && (x < r.W);
+        dst[i] = in ? make_float2(sx[y * r.W + x], sy[y * r.W + x]) : make_float2(0.f, 0.f);
+    }
 }
 
-// dual-phase packed gradient [F][P][B][phase][H][Wp] float2 -> [P][F][B][2][H][W]
 template <bool DET>
 __global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__restrict__ packed, float *__restrict__ out, int F, int P, int B,
                                                                int W, long HW, ImgGeom g) {
@@ -89,11 +95,11 @@ extern "C" int tef_pack_flow(const void *const *flow_maps_host, int F, int t, in
     if (!flow_maps_host || !packed || F < 1 || F > TEF_MAX_FLOWS || t < 0 || t >= P || B < 1) return TEF_EINVAL;
     FlowPtrs src;
     for (int f = 0; f < F; ++f) { if (!flow_maps_host[f]) return TEF_EINVAL; src.p[f] = (const float *)flow_maps_host[f]; }
-    const long HW = (long)H * W;
-    int bx = (int)((HW + kThreads - 1) / kThreads);
+    const Res r = Res::make(H, W);
+    int bx = (2 * r.fplane + kThreads - 1) / kThreads;
     if (bx > 148 * 4) bx = 148 * 4;
     ProfScope ps(K_PACK_FLOW, (cudaStream_t)stream);
-    pack_flow_kernel<<<dim3(bx, B, F), kThreads, 0, (cudaStream_t)stream>>>(src, (float2 *)packed, t, P, B, HW);
+    pack_flow_kernel<<<dim3(bx, B, F), kThreads, 0, (cudaStream_t)stream>>>(src, (float2 *)packed, t, P, B, r);
     return (int)cudaGetLastError();
 }
 

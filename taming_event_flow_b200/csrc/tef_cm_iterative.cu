@@ -41,7 +41,7 @@ namespace tef {
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
                                                int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */) {
-    const long stride = (long)p.B * p.H * p.W;     // one pass further
+    const long stride = (long)p.B * 2 * p.res.fplane;   // one pass further (dual-phase maps)
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
     const bool in0 = inside(y0, x0, p.res);
@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
-    const long HW = (long)p.H * p.W;
-    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * HW, t, e.x, e.y, e.z, pos);
+    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos);
 
     // gradient-carrying rows keep their chain for the backward kernel (coalesced 8-byte stores)
     if (set == 0 && p.posbuf) {
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
-    const long HW = (long)p.H * p.W;
+    const long HW = 2 * p.res.fplane;                              // float2 elements per (pass, sample) flow map
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
     const long gmap_sz = (DET ? 4 : 2) * p.ig.plane;               // float2 elements per (pass, sample) gradient map
     float2 *gflow_f = p.gflow + (long)f * p.P * p.B * gmap_sz;
@@ -181,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         hi_node = max(hi_node, min(w.high_tref - 1, t + w.delta));
     }
     if (!has) return;
-    // gradient images: [pol][H][Wp] float2 per slot -- the phase-0 planes of img, or gimg in deterministic mode
-    const long gslot = (DET ? 2 : 4) * p.ig.plane;
+    // gradient images: [phase][pol][H][Wp] float2 per slot -- in place in img, or gimg in deterministic mode
+    const long gslot = 4 * p.ig.plane;
     const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
-    const float2 vxy = sample_flow<false>(p.flow + (((long)f * p.P + t) * p.B + b) * HW, p.res, e.y, e.z, nullptr);
+    const float2 vxy = sample_flow<false>(p.flow + (((long)f * p.P + t) * p.B + b) * 2 * p.res.fplane, p.res, e.y, e.z, nullptr);
     const float2 v = make_float2(vxy.y, vxy.x);                        // (y, x), utils/iwe.py:38
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;
     float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
@@ -56,11 +56,11 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
-    const long mo = (((long)f * p.P + t) * p.B + b) * HW;
+    const long mo = (((long)f * p.P + t) * p.B + b) * 2 * p.res.fplane;
     Taps tp;
     const float2 vxy = sample_flow<true>(p.flow + mo, p.res, e.y, e.z, &tp);
     const float2 v = make_float2(vxy.y, vxy.x);
-    const long gslot = (DET ? 2 : 4) * p.ig.plane;
+    const long gslot = 4 * p.ig.plane;
     const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
     float gvy = 0.f, gvx = 0.f;
     for (int s = 0; s < p.sc.S; ++s) {

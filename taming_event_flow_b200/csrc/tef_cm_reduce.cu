@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constan
     const float div_a = p.linear ? 2.0f : (float)(2 * p.sc.delta[s] + 1);
     const float cf = upstream(__ldg(p.grad_out), p.F, p.sc.S, div_a, s) / p.den[image];
     float2 *im = p.img + image * (DET ? 8 : 4) * p.ig.plane;
-    float2 *out = DET ? p.gimg + image * 2 * p.ig.plane : im;     // [pol][H][Wp]; in place (phase-0 planes) unless deterministic
+    float2 *out = DET ? p.gimg + image * 4 * p.ig.plane : im;     // [phase][pol][H][Wp]; in place unless deterministic
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constan
             const float d = v.x + 1e-9f;
             const float a = v.y / d;
             const float ga = cf * (2.0f * a);
-            out[(long)pol * p.ig.plane + o] = make_float2(-(ga * (a / d)), ga / d);    // (dL/dcount, dL/dtime-weighted)
+            const float2 gv = make_float2(-(ga * (a / d)), ga / d);                    // (dL/dcount, dL/dtime-weighted)
+            out[(long)pol * p.ig.plane + o] = gv;                                      // phase 0: column x
+            out[(long)(2 + pol) * p.ig.plane + o + 1] = gv;                            // phase 1: column x + 1
         }
     }
 }
@@ -169,6 +171,6 @@ extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     out[7] = linear ? 0 : (long)p.F * (p.P + 1) * p.rows_grad * 2; // floats in posbuf (alivebuf: F * rows_grad u64)
     out[8] = p.ig.Wp;
     out[9] = p.nchunks;                                           // partial sums per image: acc_sum / acc_nnz hold F*B*slots*nchunks entries
-    out[10] = p.det ? (long)p.F * p.B * p.nslots * 2 * p.ig.plane * 2 : 0;   // floats in gimg (deterministic mode)
+    out[10] = p.det ? (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 : 0;   // floats in gimg (deterministic mode)
     return 0;
 }

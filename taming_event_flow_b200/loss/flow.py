@@ -154,7 +154,8 @@ class BaseEventWarping(torch.nn.Module):
             raise ValueError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(f0.shape)))
         if w.packed is None:
             w.shape = (F, B, H, W)
-            w.packed = w.ws.get("packed", (F, self._max_passes(), B, H, W, 2), torch.float32, f0.device)
+            Wp = (W + 3) & ~1                      # dual-phase, zero-padded maps (csrc/tef_device.cuh)
+            w.packed = w.ws.get("packed", (F, self._max_passes(), B, 2, H + 1, Wp, 2), torch.float32, f0.device)
         w.flows.append(list(flow_list))
 
     def _update_pass(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
