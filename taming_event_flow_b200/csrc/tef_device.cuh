@@ -123,7 +123,12 @@ __device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ 
     const float n_ = iy - fy0, s_ = 1.0f - n_;
     const int y0 = (int)fy0, x0 = (int)fx0;
     const float4 *p = tap_row(map, r, y0, x0);
+#ifdef TEF_EXP_NO_GATHER
+    const float4 top = make_float4(0.3f * (float)(x0 & 7), -0.2f, 0.1f, 0.4f), bot = make_float4(0.2f, 0.1f * (float)(y0 & 3), -0.3f, 0.2f);
+    if (p == nullptr) return make_float2(0.f, 0.f);
+#else
     const float4 top = __ldg(p), bot = __ldg(p + (r.Wp >> 1));
+#endif
     const float w0 = s_ * e_, w1 = s_ * w_, w2 = n_ * e_, w3 = n_ * w_;
     float ox = top.x * w0, oy = top.y * w0;
     ox = __fmaf_rn(top.z, w1, ox); oy = __fmaf_rn(top.w, w1, oy);
