@@ -342,13 +342,50 @@ class BaseEventWarping(torch.nn.Module):
             loss = loss / (nonzero.sum(1) + 1e-9)
         return loss.sum()
 
+    # Smoothness priors (upstream loss/flow.py:131-209).  Off in every shipped config (`Null` weights) and not on the
+    # accelerated path: they are evaluated on the flow tensors the caller handed to `update` with ordinary autograd
+    # (the one gather they need goes through the `get_event_flow` kernel).
+    def _flow_stack(self, f):
+        """[B, passes, 2, H, W] (ch0 = x, ch1 = y) of flow scale `f` over all passes given to `update`."""
+        return torch.stack([per_pass[f] for per_pass in self._win.flows], dim=1)
+
     def flow_spatial_smoothing(self):
-        raise NotImplementedError("flow_spat_smooth_weight is not None: the smoothness priors (upstream loss/flow.py:131-209) "
-                                  "are outside the accelerated path (SURVEY.md §8f-3)")
+        """Charbonnier penalty on horizontal, vertical and both diagonal flow differences (upstream :170-209)."""
+        eps = 1e-6
+        total = 0
+        for f in range(self._num_flows):
+            fl = self._flow_stack(f)                                            # [B,P,2,H,W]
+            pairs = ((fl[..., :, :-1], fl[..., :, 1:]), (fl[..., :-1, :], fl[..., 1:, :]),
+                     (fl[..., :-1, :-1], fl[..., 1:, 1:]), (fl[..., 1:, :-1], fl[..., :-1, 1:]))
+            acc = 0
+            for a, b in pairs:
+                d = torch.sqrt((a - b) ** 2 + eps).sum(2)                       # x and y components
+                acc = acc + d.flatten(2).mean(2).mean(1)
+            total = total + acc / 4
+        total = total / self._num_flows
+        return self.flow_spat_smooth_weight * total.sum()
 
     def flow_temporal_smoothing(self):
-        raise NotImplementedError("flow_temp_smooth_weight is not None: the smoothness priors (upstream loss/flow.py:131-209) "
-                                  "are outside the accelerated path (SURVEY.md §8f-3)")
+        """Charbonnier penalty between each flow map and the next one sampled where the flow points (upstream :131-168)."""
+        from ..utils.iwe import get_event_flow
+
+        H, W = self.res
+        dev = self._win.flows[0][0].device
+        yy, xx = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32), torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+        grid = torch.stack([yy, xx], 0).unsqueeze(0)                           # [1,2,H,W] (y, x)
+        total = 0
+        for f in range(self._num_flows):
+            fl = self._flow_stack(f)
+            B = fl.shape[0]
+            for j in range(fl.shape[1] - 1):
+                cur = torch.stack([fl[:, j, 1], fl[:, j, 0]], 1)                # (y, x) order
+                tgt = (grid + cur).reshape(B, 2, -1).permute(0, 2, 1)           # [B,HW,2]
+                inside = ((tgt[..., 0] >= 0) & (tgt[..., 0] <= H - 1.0) & (tgt[..., 1] >= 0) & (tgt[..., 1] <= W - 1.0)).float()
+                nxt = get_event_flow(fl[:, j + 1, 0], fl[:, j + 1, 1], tgt)     # [B,HW,2] (y, x)
+                diff = torch.sqrt((cur.reshape(B, 2, -1).permute(0, 2, 1) - nxt) ** 2 + 1e-9).sum(2)
+                total = total + (diff * inside).sum(1) / (inside.sum(1) + 1e-9)
+        total = total / self._num_flows / (self._passes - 1)
+        return self.flow_temp_smooth_weight * total.sum()
 
     def forward(self):
         raise NotImplementedError

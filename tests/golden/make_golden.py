@@ -96,18 +96,26 @@ LOSS_CASES = [
     ("lin_f2", "linear", 2, 4, 300, 200, 32, 32, 2, 1, "two", 3.0, False, True, 8),
     ("lin_s2_noborder", "linear", 2, 8, 300, 200, 32, 40, 1, 2, "two", 3.0, False, False, 9),
     ("lin_ragged", "linear", 2, 10, 300, 0, 32, 40, 1, 1, "two", 3.0, True, True, 10),
+    # smoothness priors switched on (flow_spat_smooth_weight, flow_temp_smooth_weight)
+    ("iter_smooth", "iterative", 2, 4, 300, 100, 32, 40, 2, 1, "two", 2.0, False, True, 11, (0.3, 0.7)),
+    ("lin_smooth", "linear", 2, 4, 300, 100, 32, 40, 1, 1, "two", 2.0, False, True, 12, (0.5, 0.25)),
 ]
 
 
 def make_loss_cases():
-    for (name, kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, seed) in LOSS_CASES:
+    for case in LOSS_CASES:
+        (name, kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, seed) = case[:15]
+        smooth = case[15] if len(case) > 15 else (None, None)
         seq = syn.make_sequence(seed, B, P, N, Nd, H, W, F, sigma, ragged)
         P_cfg = P // 2 if (mode == "four" and kind == "iterative") else P  # Iterative.__init__ doubles it (loss/flow.py:422-423)
         cfg = syn.loss_config(H, W, B, P_cfg, S, mode)
+        cfg["loss"]["flow_spat_smooth_weight"], cfg["loss"]["flow_temp_smooth_weight"] = smooth
         l32, g32, iwe32 = run_loss(kind, cfg, seq, torch.float32, border, record_iwe=True)
         l64, g64, _ = run_loss(kind, cfg, seq, torch.float64, border)
         out = {
             "kind": kind, "B": B, "P": P, "H": H, "W": W, "F": F, "S": S, "mode": mode, "border": border,
+            "smooth_spat": np.float64(smooth[0] if smooth[0] is not None else -1.0),
+            "smooth_temp": np.float64(smooth[1] if smooth[1] is not None else -1.0),
             "loss32": np.float32(l32), "loss64": np.float64(l64), "grad32": g32.astype(np.float32), "grad64": g64,
             "iwe32": iwe32.astype(np.float32),
             "flows": np.stack([np.stack([seq["flows"][t][f].numpy() for t in range(P)]) for f in range(F)]),

@@ -45,7 +45,12 @@ def _run_gpu(kind, cfg, flows, events, masks, d_events, d_masks, border=True, lo
 
 def _cfg_for(c):
     P_cfg = c["P"] // 2 if (c["mode"] == "four" and c["kind"] == "iterative") else c["P"]
-    return syn.loss_config(c["H"], c["W"], c["B"], P_cfg, c["S"], c["mode"])
+    cfg = syn.loss_config(c["H"], c["W"], c["B"], P_cfg, c["S"], c["mode"])
+    if c["smooth_spat"] >= 0:
+        cfg["loss"]["flow_spat_smooth_weight"] = float(c["smooth_spat"])
+    if c["smooth_temp"] >= 0:
+        cfg["loss"]["flow_temp_smooth_weight"] = float(c["smooth_temp"])
+    return cfg
 
 
 @pytest.mark.parametrize("name", loss_case_names())

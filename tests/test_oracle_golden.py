@@ -15,7 +15,7 @@ def _run(c, dtype):
     return fn(cfg, c["flow_list"], c["events"], c["masks"], c["d_events"], c["d_masks"], dtype, want_grad=True, want_iwe=True)
 
 
-@pytest.mark.parametrize("name", loss_case_names())
+@pytest.mark.parametrize("name", loss_case_names("cm_only"))
 def test_loss_oracle_fp64_matches_reference_fp64(name):
     c = load_loss_case(name)
     o = _run(c, np.float64)
@@ -24,7 +24,7 @@ def test_loss_oracle_fp64_matches_reference_fp64(name):
     assert linf < 1e-11 and l2 < 1e-11, (linf, l2)
 
 
-@pytest.mark.parametrize("name", loss_case_names())
+@pytest.mark.parametrize("name", loss_case_names("cm_only"))
 def test_loss_oracle_fp32_matches_reference_fp32(name):
     c = load_loss_case(name)
     o = _run(c, np.float32)

@@ -13,6 +13,8 @@ def loss_case_names(kind=None):
         names = [n for n in names if n.startswith("iter")]
     elif kind == "linear":
         names = [n for n in names if n.startswith("lin")]
+    elif kind == "cm_only":      # cases the oracle covers (it restates the CM terms, not the smoothness priors)
+        names = [n for n in names if "smooth" not in n]
     return names
 
 
@@ -21,6 +23,8 @@ def load_loss_case(name):
     z = np.load(os.path.join(GOLDEN, "loss_%s.npz" % name))
     c = {k: z[k].item() if z[k].ndim == 0 else z[k] for k in z.files if not k[:2] in ("ev", "mk") and not k[:3] in ("dev", "dmk")}
     P, F = int(c["P"]), int(c["F"])
+    c.setdefault("smooth_spat", -1.0)
+    c.setdefault("smooth_temp", -1.0)
     c["flow_list"] = [[c["flows"][f, t] for f in range(F)] for t in range(P)]
     c["events"] = [z["ev%d" % t] for t in range(P)]
     c["masks"] = [z["mk%d" % t] for t in range(P)]
