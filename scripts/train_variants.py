@@ -32,7 +32,8 @@ def run(tag, cl=False, bench_flag=False, steps=5):
     def step():
         windows = [(seq["events"][t].to(dev), masks[t][0], seq["d_events"][t].to(dev), masks[t][1]) for t in range(P)]
         return train_step(model, loss_fn, opt, windows, encode=enc)
-    for _ in range(3):
+    first = step().item()
+    for _ in range(2):
         step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -40,7 +41,7 @@ def run(tag, cl=False, bench_flag=False, steps=5):
         l = step()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
-    print("%-28s %.2f ms/step  %.0f windows/s  loss %.5f" % (tag, dt * 1e3, wl["B"] * P / dt, l.item()))
+    print("%-28s %.2f ms/step  %.0f windows/s  first loss %.5f  loss after 8 steps %.5f" % (tag, dt * 1e3, wl["B"] * P / dt, first, l.item()))
 
 run("baseline")
 run("cudnn.benchmark", bench_flag=True)

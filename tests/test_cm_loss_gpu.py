@@ -266,3 +266,27 @@ def test_deterministic_mode_is_order_independent_and_bit_reproducible(kind):
     assert rel_err(runs[0]["iwe"], o["iwe"])[0] < TOL
     assert np.array_equal(runs[0]["iwe"] != 0, o["iwe"] != 0)
     assert rel_err(runs[0]["gflow"], o["gflow"])[0] < TOL
+
+
+def test_non_contiguous_inputs_are_handled():
+    """Flow maps in channels_last memory format (what a channels_last network emits), sliced event tensors and a
+    non-float mask give the same loss and gradients as contiguous fp32 inputs."""
+    B, P, N, H, W = 2, 4, 2000, 48, 64
+    seq = syn.make_sequence(31, B, P, N, 300, H, W, 2, 2.0)
+    cfg = syn.loss_config(H, W, B, P)
+    ref = _run_gpu("iterative", cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
+    m = _module("iterative", cfg)
+    flows = [[f.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in per] for per in seq["flows"]]
+    for t in range(P):
+        wide = torch.zeros(B, N, 6, device="cuda")
+        wide[:, :, 1:5] = seq["events"][t].cuda()
+        ev = wide[:, :, 1:5]                                     # a strided view: the in-place ts update must land in `wide`
+        assert not ev.is_contiguous()
+        m.update([f * 1.0 for f in flows[t]], ev, seq["masks"][t].cuda().double(), seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+        assert not (flows[t][0] * 1.0).is_contiguous()
+        assert torch.equal(wide[:, :, 1].cpu(), seq["events"][t][:, :, 0] + t)
+    loss = m()
+    loss.backward()
+    g = np.stack([np.stack([flows[t][f].grad.cpu().numpy() for t in range(P)]) for f in range(2)])
+    assert abs(loss.item() - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert rel_err(g, ref["gflow"])[0] < 1e-6
