@@ -477,6 +477,17 @@ def run_ours(args, wl):
                                     "ms_reds_at_peak": round(t_r * 1e3, 4), "bound": "gather" if t_g >= t_r else "red",
                                     "frac": round(t_min * 1e3 / kern[k]["ms_avg"], 4)}
         cpu = run_cpu_baseline(wl)
+    # the second half of BASELINE.json's metric ("train windows/s"): a short run of the training-step workload
+    # (PyTorch network + CM loss + SUM all-reduce), reported as an extra key of the same line
+    train = None
+    if os.environ.get("TEF_BENCH_TRAIN", "1") != "0":
+        try:
+            targs = argparse.Namespace(steps=min(args.steps, 5), warmup=3)
+            train = run_train(targs, dict(TRAIN_WORKLOADS["train_128x128_b8"], name="train_128x128_b8"), quiet=True)
+            train = {k: train[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config")}
+        except Exception as exc:      # the extra must never take the headline number down
+            train = {"error": repr(exc)[:200]}
+    if rank == 0:
         line = {
             "metric": "cm_loss_fwd_bwd_throughput", "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -485,7 +496,7 @@ def run_ours(args, wl):
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "cpu_baseline": cpu,
             "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"], "share_of_step": round(v["ms_total"] / ms, 4)} for k, v in kern.items()},
-            "loss": loss_value, "events_per_step_per_gpu": E,
+            "loss": loss_value, "events_per_step_per_gpu": E, "train_step": train,
         }
         print(json.dumps(line))
     if world > 1:

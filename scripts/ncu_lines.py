@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
+    mangled = kern + "ILb0E" if not kern.endswith("E") else kern          # templated kernels: the non-deterministic instance
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     so = os.path.join(ROOT, "taming_event_flow_b200", "libtef_b200.so")
     tmp = tempfile.mkdtemp()
@@ -25,7 +26,7 @@ def main():
     lines = None
     for cub in glob.glob(os.path.join(tmp, "*.cubin")):
         out = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-        m = re.search(r"\.text\.(\S*%s\S*):\n(.*?)(?=\n//-{10,}|\Z)" % kern, out, re.S)
+        m = re.search(r"\.text\.(\S*%s\S*):\n(.*?)(?=\n//-{10,}|\Z)" % mangled, out, re.S)
         if m:
             lines = m.group(2).splitlines()
             break
@@ -43,6 +44,8 @@ def main():
     hdr = rows[1]
     data = rows[2:]
     iE, iW = hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
+    if len(data) > len(table):
+        data = data[:len(table)]
     if len(data) != len(table):
         print("WARNING: %d SASS instructions in the report vs %d in the library (different build?)" % (len(data), len(table)))
     n = min(len(data), len(table))

@@ -234,7 +234,8 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
         const int off = (int)c.cy[ky] * g.Wp + col;
         const float tl = wl * nts, tr = wr * nts;
         if (!DET) {
-            red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
+            if (mv == 1.0f) red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl, tl, wr, tr);      // x * 1 == x: skip the products
+            else red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
             if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
         } else {
             for (int q = pol; q < (both ? 2 : pol + 1); ++q) {

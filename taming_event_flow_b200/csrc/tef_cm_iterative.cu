@@ -40,7 +40,8 @@ namespace tef {
 // The pass index t is uniform per CTA, so the loop bounds do not diverge.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
-                                               int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */) {
+                                               int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */,
+                                               float2 *__restrict__ pb /* this row of posbuf (stride rows_grad) or nullptr */) {
     const long stride = (long)p.B * 2 * p.res.fplane;   // one pass further (dual-phase maps)
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
@@ -60,6 +61,7 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
         }
         tprev = (float)tr;
         *pw = make_float2(y, x);
+        if (pb) pb[(long)tr * p.rows_grad] = make_float2(y, x);      // coalesced 8-byte store, kept for the backward kernel
     }
     y = y0; x = x0; tprev = ts; al = true; safe = in0;
     map = flow_fb + (long)t * stride;
@@ -75,6 +77,7 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
         }
         tprev = (float)tr;
         *pw = make_float2(y, x);
+        if (pb) pb[(long)tr * p.rows_grad] = make_float2(y, x);
     }
     return alive;
 }
@@ -109,14 +112,10 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
-    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos);
-
-    // gradient-carrying rows keep their chain for the backward kernel (coalesced 8-byte stores)
-    if (set == 0 && p.posbuf) {
-        float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
-        for (int tr = 0; tr <= p.P; ++tr) pb[(long)tr * p.rows_grad] = pos[tr * kThreads + threadIdx.x];
-        p.alivebuf[(long)f * p.rows_grad + row] = alive;
-    }
+    // gradient-carrying rows keep their chain for the backward kernel
+    float2 *pb = (set == 0 && p.posbuf) ? p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row : nullptr;
+    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb);
+    if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
 
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;          // float2 elements per slot (int64 pairs in deterministic mode)
     float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
