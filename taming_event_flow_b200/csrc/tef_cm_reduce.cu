@@ -64,25 +64,28 @@ __global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__re
     }
 }
 
-// one CTA: den = nnz + 1e-9 (:127), loss = sum over flow maps, scales, windows, trefs, samples
+// one CTA, one warp per image: den = nnz + 1e-9 (:127), loss = sum over flow maps, scales, windows, trefs, samples.
+// Every sum has a fixed order (lane-strided partials, shuffle tree, warps in order): bit-reproducible.
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constant__ CmParams p) {
     const int nimg = p.F * p.B * p.nslots;
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < nimg; i += kThreads) {
-        const int q = i % p.nslots;
-        const int s = scale_of_slot(p.sc, q);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double acc = 0.0;                                   // lane 0 of each warp accumulates its images
+    for (int i = wid; i < nimg; i += kThreads / 32) {
         double sum = 0.0; int nnz = 0;
-        for (int c = 0; c < p.nchunks; ++c) { sum += p.acc_sum[(long)i * p.nchunks + c]; nnz += p.acc_nnz[(long)i * p.nchunks + c]; }
-        const float den = p.loss_scaling ? ((float)nnz + 1e-9f) : 1.0f;
-        p.den[i] = den;
-        const double div_a = p.linear ? 2.0 : (double)(2 * p.sc.delta[s] + 1);
-        acc += sum / (double)den / (double)(1 << s) / div_a / (double)p.sc.S / (double)p.F;
-    }
-    // fixed-order tree: shuffle reduction inside each warp, then warps in order
+        for (int c = lane; c < p.nchunks; c += 32) { sum += p.acc_sum[(long)i * p.nchunks + c]; nnz += p.acc_nnz[(long)i * p.nchunks + c]; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
+        if (lane == 0) {
+            const int q = i % p.nslots;
+            const int s = scale_of_slot(p.sc, q);
+            const float den = p.loss_scaling ? ((float)nnz + 1e-9f) : 1.0f;
+            p.den[i] = den;
+            const double div_a = p.linear ? 2.0 : (double)(2 * p.sc.delta[s] + 1);
+            acc += sum / (double)den / (double)(1 << s) / div_a / (double)p.sc.S / (double)p.F;
+        }
+    }
     __shared__ double s_acc[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+    if (lane == 0) s_acc[wid] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0;
