@@ -179,7 +179,7 @@ __device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b,
     if (row >= hi) return false;
     float m2, m3;
     // one 256-bit load per event (LDG.E.ENL2.256): the whole 32-byte sorted record
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w), "=f"(m.x), "=f"(m.y), "=f"(m2), "=f"(m3)
                  : "l"(p.sort.rec + 2 * (long)row));
     b = __float_as_int(e.w);

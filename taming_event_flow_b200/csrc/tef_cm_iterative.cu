@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
         }
         tprev = (float)tr;
         *pw = make_float2(y, x);
-        if (pb) pb[(long)tr * p.rows_grad] = make_float2(y, x);      // coalesced 8-byte store, kept for the backward kernel
+        if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));   // coalesced streaming store (evict-first), kept for the backward kernel
     }
     y = y0; x = x0; tprev = ts; al = true; safe = in0;
     map = flow_fb + (long)t * stride;
@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
         }
         tprev = (float)tr;
         *pw = make_float2(y, x);
-        if (pb) pb[(long)tr * p.rows_grad] = make_float2(y, x);
+        if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));
     }
     return alive;
 }
@@ -199,10 +199,10 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     float cy_ = 0.f, cx_ = 0.f;
     {
         int tr = min(hi_node, p.P);
-        float2 q = (tr >= t + 1) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        float2 q = (tr >= t + 1) ? __ldcs(pb + (long)tr * p.rows_grad) : make_float2(0.f, 0.f);
         for (; tr >= t + 1; --tr) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr - 1) * p.rows_grad];
+            const float2 src = first ? make_float2(y0, x0) : __ldcs(pb + (long)(tr - 1) * p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -220,10 +220,10 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     cy_ = 0.f; cx_ = 0.f;
     {
         int tr = max(lo_node, 0);
-        float2 q = (tr <= t) ? pb[(long)tr * p.rows_grad] : make_float2(0.f, 0.f);
+        float2 q = (tr <= t) ? __ldcs(pb + (long)tr * p.rows_grad) : make_float2(0.f, 0.f);
         for (; tr <= t; ++tr) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(y0, x0) : pb[(long)(tr + 1) * p.rows_grad];
+            const float2 src = first ? make_float2(y0, x0) : __ldcs(pb + (long)(tr + 1) * p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
