@@ -214,6 +214,16 @@ __device__ __forceinline__ float2 *img_plane(float2 *slot_base, const ImgGeom &g
 // (w_left, w_left*n, w_right, w_right*n) into the plane of the event's polarity.
 // Corner coordinates, weights and in-image tests are exactly get_interpolation's (utils/iwe.py:85-107);
 // a corner outside the image (or with weight 0) contributes an exact +0.
+// Masks with both polarities non-zero never come out of the reference's loader ({0,1} masks); the extra work for them
+// sits in non-inlined functions, so that the common case does not even issue predicated-off instructions.
+static __device__ __noinline__ void splat_second_polarity(float2 *plane1, float wl, float tl, float wr, float tr, float my) {
+    red_add_v4(plane1, wl * my, tl * my, wr * my, tr * my);
+}
+static __device__ __noinline__ void grad_second_polarity(const float2 *plane1, float nts, float my, float &gl, float &gr) {
+    const float4 u = __ldg(reinterpret_cast<const float4 *>(plane1));
+    gl = gl + my * (u.x + nts * u.y); gr = gr + my * (u.z + nts * u.w);
+}
+
 template <bool INSIDE, bool DET>
 __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res &r, const ImgGeom &g, float y, float x, float nts, float2 m) {
     Corners c;
@@ -236,7 +246,7 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
         if (!DET) {
             if (mv == 1.0f) red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl, tl, wr, tr);      // x * 1 == x: skip the products
             else red_add_v4(img_plane(slot_base, g, phase, pol) + off, wl * mv, tl * mv, wr * mv, tr * mv);
-            if (both) red_add_v4(img_plane(slot_base, g, phase, 1) + off, wl * m.y, tl * m.y, wr * m.y, tr * m.y);
+            if (both) splat_second_polarity(img_plane(slot_base, g, phase, 1) + off, wl, tl, wr, tr, m.y);
         } else {
             for (int q = pol; q < (both ? 2 : pol + 1); ++q) {
                 const float mq = q ? m.y : m.x;
@@ -278,10 +288,7 @@ __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, c
         const int off = (int)c.cy[ky] * g.Wp + col;
         const float4 v = __ldg(reinterpret_cast<const float4 *>(g0 + off));
         float gl = m0 * (v.x + nts * v.y), gr = m0 * (v.z + nts * v.w);
-        if (!binary) {
-            const float4 u = __ldg(reinterpret_cast<const float4 *>(slot_base + (long)(phase * 2 + 1) * g.plane + off));
-            gl = gl + m.y * (u.x + nts * u.y); gr = gr + m.y * (u.z + nts * u.w);
-        }
+        if (!binary) grad_second_polarity(slot_base + (long)(phase * 2 + 1) * g.plane + off, nts, m.y, gl, gr);
         if (c.okx[0]) { gy += gl * dy[ky] * c.wx[0]; gx += gl * c.wy[ky] * dx[0]; }
         if (c.okx[1]) { gy += gr * dy[ky] * c.wx[1]; gx += gr * c.wy[ky] * dx[1]; }
     }

@@ -82,53 +82,66 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
     return alive;
 }
 
-// sub-window bookkeeping of one temporal scale for an event of pass t (loss/flow.py:657-686)
-struct Win {
-    int lo, hi, low_tref, high_tref, delta, slot0;
-    bool shared_ok;
+// Sub-window bookkeeping of one temporal scale for the events of pass t (loss/flow.py:657-686).  The pass index is
+// uniform per CTA, so the table is built once per CTA in shared memory (no per-thread integer division):
+// tr0..tr1 = reference times this pass feeds at the scale (max(lo, tr-delta) <= t < min(hi, tr+delta), :685-686),
+// mask = reference times whose in-image bits form the shared border mask (:671-681).
+struct WinS {
+    int valid, tr0, tr1, slot0;
+    uint32_t mask;
+    float fdelta, rdelta;
 };
-__device__ __forceinline__ bool window_of(const CmParams &p, int s, int t, uint32_t alive, Win &w) {
-    const int L = p.sc.L[s];
-    if (t >= (L << s)) return false;               // passes beyond 2^s windows are unused at this scale
-    const int wi = t / L;
-    w.delta = p.sc.delta[s];
-    w.lo = wi * L; w.hi = w.lo + L;
-    w.low_tref = w.lo; w.high_tref = w.hi + 1;
-    if (p.mode == 4) { w.low_tref = w.lo + w.delta; w.high_tref = w.lo + 3 * w.delta + 1; }
-    const uint32_t m = (uint32_t)((1ull << w.high_tref) - 1ull) & ~((1u << w.low_tref) - 1u);
-    w.shared_ok = (alive & m) == m;                // product of the masks over all tref (:671-681)
-    w.slot0 = p.sc.slot_base[s] + wi * p.sc.ntau[s] - w.low_tref;
-    return true;
+__device__ __forceinline__ void build_windows(const CmParams &p, int t, WinS *sw) {
+    const int s = threadIdx.x;
+    if (s < p.sc.S) {
+        WinS w;
+        const int L = p.sc.L[s];
+        w.valid = t < (L << s);                    // passes beyond 2^s windows are unused at this scale
+        const int wi = t / L, delta = p.sc.delta[s];
+        const int lo = wi * L, hi = lo + L;
+        int low_tref = lo, high_tref = hi + 1;
+        if (p.mode == 4) { low_tref = lo + delta; high_tref = lo + 3 * delta + 1; }
+        w.mask = (uint32_t)((1ull << high_tref) - 1ull) & ~((1u << low_tref) - 1u);
+        w.tr0 = max(low_tref, t - delta + 1); w.tr1 = min(high_tref - 1, t + delta);
+        w.slot0 = p.sc.slot_base[s] + wi * p.sc.ntau[s] - low_tref;
+        w.fdelta = (float)delta; w.rdelta = 1.0f / w.fdelta;
+        sw[s] = w;
+    }
+    __syncthreads();
 }
-__device__ __forceinline__ bool feeds(const Win &w, int tr, int t) {
-    if (tr < w.low_tref || tr >= w.high_tref) return false;
-    const int lo_e = max(w.lo, tr - w.delta), hi_e = min(w.hi, tr + w.delta);   // :685-686
-    return t >= lo_e && t < hi_e;
+// scales at which this event is splatted: inside a sub-window and, with border compensation, alive at all its reference times
+__device__ __forceinline__ uint32_t active_scales(const CmParams &p, const WinS *sw, uint32_t alive) {
+    uint32_t has = 0;
+    for (int s = 0; s < p.sc.S; ++s)
+        if (sw[s].valid && (!p.border || (alive & sw[s].mask) == sw[s].mask)) has |= 1u << s;
+    return has;
 }
 
 template <bool DET>
 __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
+    __shared__ WinS sw[TEF_MAX_SCALES];
     int t, b, row, set; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m, row, set)) return;
+    const bool live = locate_sorted(p, t, b, e, m, row, set);
+    build_windows(p, t, sw);
+    if (!live) return;
     const int f = blockIdx.y;
+
     // gradient-carrying rows keep their chain for the backward kernel
     float2 *pb = (set == 0 && p.posbuf) ? p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row : nullptr;
     const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb);
     if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
 
+    const uint32_t has = active_scales(p, sw, alive);
+    if (!has) return;
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;          // float2 elements per slot (int64 pairs in deterministic mode)
     float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
     for (int s = 0; s < p.sc.S; ++s) {
-        Win w;
-        if (!window_of(p, s, t, alive, w)) continue;
-        if (p.border && !w.shared_ok) continue;
-        const float fdelta = (float)w.delta, rdelta = 1.0f / fdelta;
-        // reference times fed by window t: max(lo, tr-delta) <= t < min(hi, tr+delta)  (:685-686)
-        const int tr0 = max(w.low_tref, t - w.delta + 1), tr1 = min(w.high_tref - 1, t + w.delta);
-        for (int tr = tr0; tr <= tr1; ++tr) {
+        if (!((has >> s) & 1u)) continue;
+        const WinS w = sw[s];
+        for (int tr = w.tr0; tr <= w.tr1; ++tr) {
             if (!p.border && !((alive >> tr) & 1u)) continue;
-            const float nts = 1.0f - div_const(fabsf((float)tr - e.x), fdelta, rdelta);   // loss/flow.py:94-95
+            const float nts = 1.0f - div_const(fabsf((float)tr - e.x), w.fdelta, w.rdelta);   // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
             splat<true, DET>(img_fb + (long)(w.slot0 + tr) * slot_stride, p.res, p.ig, q.x, q.y, nts, m);
         }
@@ -156,8 +169,11 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
 // next node, reduce into the packed flow-gradient map and step towards the event's own window.
 template <bool DET>
 __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(const __grid_constant__ CmParams p) {
+    __shared__ WinS sw[TEF_MAX_SCALES];
     int t, b, row, set; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m, row, set)) return;
+    const bool live = locate_sorted(p, t, b, e, m, row, set);
+    build_windows(p, t, sw);
+    if (!live) return;
     const int f = blockIdx.y;
     const long HW = 2 * p.res.fplane;                              // float2 elements per (pass, sample) flow map
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
@@ -168,30 +184,20 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
 
     // scales whose sub-window takes this event, and the range of nodes that receive an image gradient
-    int lo_node = p.P + 1, hi_node = -1;
-    uint32_t has = 0;
-    for (int s = 0; s < p.sc.S; ++s) {
-        Win w;
-        if (!window_of(p, s, t, alive, w)) continue;
-        if (p.border && !w.shared_ok) continue;
-        has |= 1u << s;
-        lo_node = min(lo_node, max(w.low_tref, t - w.delta + 1));
-        hi_node = max(hi_node, min(w.high_tref - 1, t + w.delta));
-    }
+    const uint32_t has = active_scales(p, sw, alive);
     if (!has) return;
+    int lo_node = p.P + 1, hi_node = -1;
+    for (int s = 0; s < p.sc.S; ++s)
+        if ((has >> s) & 1u) { lo_node = min(lo_node, sw[s].tr0); hi_node = max(hi_node, sw[s].tr1); }
     // gradient images: [phase][pol][H][Wp] float2 per slot -- in place in img, or gimg in deterministic mode
     const long gslot = 4 * p.ig.plane;
     const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
 
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         for (int s = 0; s < p.sc.S; ++s) {
-            if (!((has >> s) & 1u)) continue;
-            Win w;
-            window_of(p, s, t, alive, w);
-            if (!feeds(w, tr, t)) continue;
-            const float fdelta = (float)w.delta;
-            const float nts = 1.0f - div_const(fabsf((float)tr - ts), fdelta, 1.0f / fdelta);
-            iwe_grad<true>(img_fb + (long)(w.slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+            if (!((has >> s) & 1u) || tr < sw[s].tr0 || tr > sw[s].tr1) continue;
+            const float nts = 1.0f - div_const(fabsf((float)tr - ts), sw[s].fdelta, sw[s].rdelta);
+            iwe_grad<true>(img_fb + (long)(sw[s].slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
         }
     };
 
