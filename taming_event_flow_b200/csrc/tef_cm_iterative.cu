@@ -201,14 +201,18 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         }
     };
 
+    const long map_stride = (long)p.B * HW, gmap_stride = (long)p.B * gmap_sz;
     // reverse of the forward chain: nodes hi_node .. t+1 (nodes beyond carry no gradient)
     float cy_ = 0.f, cx_ = 0.f;
     {
         int tr = min(hi_node, p.P);
-        float2 q = (tr >= t + 1) ? __ldcs(pb + (long)tr * p.rows_grad) : make_float2(0.f, 0.f);
-        for (; tr >= t + 1; --tr) {
+        const float2 *pq = pb + (long)tr * p.rows_grad;                  // position of node tr; one row_grad back: node tr-1
+        const float2 *map = flow_f + (long)(tr - 1) * map_stride + (long)b * HW;
+        float2 *gmap = gflow_f + (long)(tr - 1) * gmap_stride + (long)b * gmap_sz;
+        float2 q = (tr >= t + 1) ? __ldcs(pq) : make_float2(0.f, 0.f);
+        for (; tr >= t + 1; --tr, pq -= p.rows_grad, map -= map_stride, gmap -= gmap_stride) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(y0, x0) : __ldcs(pb + (long)(tr - 1) * p.rows_grad);
+            const float2 src = first ? make_float2(y0, x0) : __ldcs(pq - p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -216,8 +220,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : 1.0f;
-                const long mo = (long)(tr - 1) * p.B + b;
-                step_bwd<DET>(flow_f + mo * HW, gflow_f + mo * gmap_sz, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
@@ -226,10 +229,13 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     cy_ = 0.f; cx_ = 0.f;
     {
         int tr = max(lo_node, 0);
-        float2 q = (tr <= t) ? __ldcs(pb + (long)tr * p.rows_grad) : make_float2(0.f, 0.f);
-        for (; tr <= t; ++tr) {
+        const float2 *pq = pb + (long)tr * p.rows_grad;
+        const float2 *map = flow_f + (long)tr * map_stride + (long)b * HW;
+        float2 *gmap = gflow_f + (long)tr * gmap_stride + (long)b * gmap_sz;
+        float2 q = (tr <= t) ? __ldcs(pq) : make_float2(0.f, 0.f);
+        for (; tr <= t; ++tr, pq += p.rows_grad, map += map_stride, gmap += gmap_stride) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(y0, x0) : __ldcs(pb + (long)(tr + 1) * p.rows_grad);
+            const float2 src = first ? make_float2(y0, x0) : __ldcs(pq + p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -237,8 +243,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : -1.0f;
-                const long mo = (long)tr * p.B + b;
-                step_bwd<DET>(flow_f + mo * HW, gflow_f + mo * gmap_sz, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }

@@ -64,17 +64,19 @@ __global__ void __launch_bounds__(kThreads) iwe_reduce_kernel(const float2 *__re
     }
 }
 
-// one CTA, one warp per image: den = nnz + 1e-9 (:127), loss = sum over flow maps, scales, windows, trefs, samples.
-// Every sum has a fixed order (lane-strided partials, shuffle tree, warps in order): bit-reproducible.
+// One CTA.  den = nnz + 1e-9 (:127), loss = sum over flow maps, scales, windows, trefs, samples.  A group of G lanes
+// (G = 32 for large images with many partial sums, 1 for small ones) owns one image; every sum has a fixed order
+// (lane-strided partials, shuffle tree, groups in order): bit-reproducible.
+template <int G>
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constant__ CmParams p) {
     const int nimg = p.F * p.B * p.nslots;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double acc = 0.0;                                   // lane 0 of each warp accumulates its images
-    for (int i = wid; i < nimg; i += kThreads / 32) {
+    const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+    double acc = 0.0;                                   // lane 0 of each group accumulates its images
+    for (int i = grp; i < nimg; i += kThreads / G) {
         double sum = 0.0; int nnz = 0;
-        for (int c = lane; c < p.nchunks; c += 32) { sum += p.acc_sum[(long)i * p.nchunks + c]; nnz += p.acc_nnz[(long)i * p.nchunks + c]; }
+        for (int c = lane; c < p.nchunks; c += G) { sum += p.acc_sum[(long)i * p.nchunks + c]; nnz += p.acc_nnz[(long)i * p.nchunks + c]; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
+        for (int o = G / 2; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
         if (lane == 0) {
             const int q = i % p.nslots;
             const int s = scale_of_slot(p.sc, q);
@@ -84,14 +86,14 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
             acc += sum / (double)den / (double)(1 << s) / div_a / (double)p.sc.S / (double)p.F;
         }
     }
-    __shared__ double s_acc[kThreads / 32];
-    if (lane == 0) s_acc[wid] = acc;
+    __shared__ double s_acc[kThreads];
+    s_acc[threadIdx.x] = (lane == 0) ? acc : 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0;
-        for (int k = 0; k < kThreads / 32; ++k) a += s_acc[k];
-        *p.loss = (float)a;
+    for (int o = kThreads / 2; o > 0; o >>= 1) {        // fixed-order tree
+        if (threadIdx.x < o) s_acc[threadIdx.x] += s_acc[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *p.loss = (float)s_acc[0];
 }
 
 // in place: (cnt, ts) -> (dL/dcnt, dL/dts) per polarity, in autograd's operation order
@@ -135,7 +137,11 @@ int tef_reduce_and_finalize(const CmParams &p, cudaStream_t st) {
         if (p.det) iwe_reduce_kernel<true><<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig);
         else iwe_reduce_kernel<false><<<grid, kThreads, 0, st>>>(p.img, p.acc_sum, p.acc_nnz, p.W, HW, p.ig);
     }
-    { ProfScope ps(K_FINALIZE, st); finalize_kernel<<<1, kThreads, 0, st>>>(p); }
+    {
+        ProfScope ps(K_FINALIZE, st);
+        if (p.nchunks >= 32) finalize_kernel<32><<<1, kThreads, 0, st>>>(p);
+        else finalize_kernel<1><<<1, kThreads, 0, st>>>(p);
+    }
     return (int)cudaGetLastError();
 }
 
