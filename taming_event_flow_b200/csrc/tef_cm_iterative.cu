@@ -148,16 +148,13 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
     }
 }
 
-// one reverse chain step, in two halves so that the tap gathers of the step are in flight
-// while the gradient images of the node are gathered: step_taps issues the loads, step_finish reduces dL/dmap and
-// returns dL/d(source position)
-__device__ __forceinline__ void step_taps(const float2 *__restrict__ map, const Res &r, float sy, float sx, Taps &tp) {
+// one reverse chain step: reduce dL/dmap, return dL/d(source position)
+template <bool DET>
+__device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
+                                         float sx, float dt, float gpy, float gpx, float &cy_, float &cx_) {
+    Taps tp;
     if (inside(sy, sx, r)) sample_flow_inside<true>(map, r, sy, sx, &tp);
     else sample_flow<true>(map, r, sy, sx, &tp);
-}
-template <bool DET>
-__device__ __forceinline__ void step_finish(const Taps &tp, float2 *__restrict__ gmap, const ImgGeom &g, float dt, float gpy, float gpx,
-                                            float &cy_, float &cx_) {
     taps_red<DET>(gmap, g, tp, dt, gpy, gpx);
     const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
     const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
@@ -217,16 +214,14 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             const bool first = (tr - 1 == t);
             const float2 src = first ? make_float2(y0, x0) : __ldcs(pq - p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
-            float gpy = 0.f, gpx = 0.f;
-            if (al) {
-                Taps tp;
-                step_taps(map, p.res, src.x, src.y, tp);
-                float gy = 0.f, gx = 0.f;
-                node_grad(tr, q, gy, gx);
-                gpy = gy + cy_; gpx = gx + cx_;
-                cy_ = 0.f; cx_ = 0.f;
-                if (gpy != 0.f || gpx != 0.f) step_finish<DET>(tp, gmap, p.ig, first ? ((float)tr - ts) : 1.0f, gpy, gpx, cy_, cx_);
-            } else { cy_ = 0.f; cx_ = 0.f; }
+            float gy = 0.f, gx = 0.f;
+            if (al) node_grad(tr, q, gy, gx);
+            const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+            cy_ = 0.f; cx_ = 0.f;
+            if (gpy != 0.f || gpx != 0.f) {
+                const float dt = first ? ((float)tr - ts) : 1.0f;
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            }
             q = src;
         }
     }
@@ -242,16 +237,14 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             const bool first = (tr == t);
             const float2 src = first ? make_float2(y0, x0) : __ldcs(pq + p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
-            float gpy = 0.f, gpx = 0.f;
-            if (al) {
-                Taps tp;
-                step_taps(map, p.res, src.x, src.y, tp);
-                float gy = 0.f, gx = 0.f;
-                node_grad(tr, q, gy, gx);
-                gpy = gy + cy_; gpx = gx + cx_;
-                cy_ = 0.f; cx_ = 0.f;
-                if (gpy != 0.f || gpx != 0.f) step_finish<DET>(tp, gmap, p.ig, first ? ((float)tr - ts) : -1.0f, gpy, gpx, cy_, cx_);
-            } else { cy_ = 0.f; cx_ = 0.f; }
+            float gy = 0.f, gx = 0.f;
+            if (al) node_grad(tr, q, gy, gx);
+            const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
+            cy_ = 0.f; cx_ = 0.f;
+            if (gpy != 0.f || gpx != 0.f) {
+                const float dt = first ? ((float)tr - ts) : -1.0f;
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+            }
             q = src;
         }
     }
