@@ -155,6 +155,10 @@ int tef_events_to_image(const float *xs, const float *ys, const float *ps, float
 int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, void *stream);
 /* batched events_to_channels over the loader's zero-padded [B][N][4] (ts, y, x, p) rows: out [B][2][H][W] */
 int tef_events_to_channels_batched(const float *events, float *out, int B, int N, int H, int W, void *stream);
+/* get_hot_event_mask: NOT in this reference (north_star names it) -- "parity unpinned".  Implements the
+   published routine of tudelft/event_flow's dataloader/encodings.py: with idx > min_obvs, up to max_px times the arg-max of
+   event_rate [H][W] is zeroed and masked while it exceeds max_rate.  event_rate is modified in place like there. */
+int tef_get_hot_event_mask(float *event_rate, float *mask, int H, int W, int idx, int max_px, int min_obvs, float max_rate, void *stream);
 /* events_to_voxel (:32-56): out [bins][H][W] */
 int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
 

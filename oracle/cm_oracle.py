@@ -229,3 +229,12 @@ def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240), dtype=np.f
     out = np.zeros((num_bins,) + tuple(sensor_size), dtype)
     getattr(lib(), "orc_events_to_voxel_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ts), _ptr(ps), _ptr(out), ctypes.c_long(xs.size), int(num_bins), int(sensor_size[0]), int(sensor_size[1]))
     return out
+
+
+def get_hot_event_mask(event_rate, idx, max_px=100, min_obvs=5, max_rate=0.8, dtype=np.float32):
+    """PARITY UNPINNED: not in the reference; restates tudelft/event_flow's published routine.  Returns (mask, updated rate)."""
+    rate = _np(event_rate, dtype).copy()
+    mask = np.zeros_like(rate)
+    ct = ctypes.c_float if dtype == np.float32 else ctypes.c_double
+    getattr(lib(), "orc_get_hot_event_mask_" + _sfx(dtype))(_ptr(rate), _ptr(mask), int(rate.size), int(idx), int(max_px), int(min_obvs), ct(max_rate))
+    return mask, rate

@@ -837,3 +837,16 @@ void FN(orc_events_to_voxel)(const REAL *xs, const REAL *ys, const REAL *ts, con
         out[(size_t)b * HW + (size_t)(long)ys[i] * W + (long)xs[i]] += ps[i] * wgt;
     }
 }
+
+/* get_hot_event_mask -- NOT in the reference: PARITY UNPINNED.  Restates the published routine of tudelft/event_flow
+   (dataloader/encodings.py): sequential arg-max (first index on ties) while the rate exceeds max_rate. */
+void FN(orc_get_hot_event_mask)(REAL *rate, REAL *mask, int n, int idx, int max_px, int min_obvs, REAL max_rate)
+{
+    for (int i = 0; i < n; ++i) mask[i] = (REAL)1;
+    if (!(idx > min_obvs)) return;
+    for (int r = 0; r < max_px; ++r) {
+        int bi = 0;
+        for (int i = 1; i < n; ++i) if (rate[i] > rate[bi]) bi = i;
+        if (rate[bi] > max_rate) { rate[bi] = (REAL)0; mask[bi] = (REAL)0; } else break;
+    }
+}

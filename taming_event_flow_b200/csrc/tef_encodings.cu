@@ -74,6 +74,43 @@ __global__ void __launch_bounds__(kThreads) to_channels_batched_kernel(const flo
     if (mneg != 0.f) red_add_f32(o + (long)H * W + px, p * mneg);
 }
 
+// Hot-pixel mask.  NOT in the reference ("parity unpinned"); the specification implemented here is the
+// published routine of the sibling code base (tudelft/event_flow, dataloader/encodings.py: get_hot_event_mask):
+//   mask = 1 everywhere; if idx > min_obvs: up to max_px times { take the arg-max of event_rate (lowest flat index on
+//   ties); if its rate > max_rate: zero the rate there and clear the mask bit, else stop }.
+// One CTA: every round is a block-wide arg-max over the (small) rate image.
+__global__ void __launch_bounds__(1024) hot_mask_kernel(float *__restrict__ rate, float *__restrict__ mask, int n, int max_px, float max_rate, int active) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    __shared__ int s_stop;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mask[i] = 1.0f;
+    if (!active) return;
+    __syncthreads();
+    for (int round = 0; round < max_px; ++round) {
+        float bv = -INFINITY; int bi = n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float v = rate[i];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+                if (s_v[k] > bv || (s_v[k] == bv && s_i[k] < bi)) { bv = s_v[k]; bi = s_i[k]; }
+            s_stop = !(bi < n && bv > max_rate);
+            if (!s_stop) { rate[bi] = 0.0f; mask[bi] = 0.0f; }
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+}
+
 }  // namespace tef
 
 using namespace tef;
@@ -115,5 +152,11 @@ extern "C" int tef_events_to_channels_batched(const float *events, float *out, i
     if (!events) return TEF_EINVAL;
     ProfScope pr(K_ENCODING, ST);
     to_channels_batched_kernel<<<TEF_GRID((long)B * N), kThreads, 0, ST>>>((const float4 *)events, out, B, N, H, W);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_get_hot_event_mask(float *event_rate, float *mask, int H, int W, int idx, int max_px, int min_obvs, float max_rate, void *stream) {
+    if (!event_rate || !mask || H < 1 || W < 1 || max_px < 0) return TEF_EINVAL;
+    ProfScope pr(K_ENCODING, ST);
+    hot_mask_kernel<<<1, 1024, 0, ST>>>(event_rate, mask, H * W, max_px, max_rate, idx > min_obvs ? 1 : 0);
     return (int)cudaGetLastError();
 }

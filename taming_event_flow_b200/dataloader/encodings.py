@@ -62,3 +62,18 @@ def events_to_channels_batched(event_list, sensor_size):
     out = torch.empty((B, 2, H, W), dtype=torch.float32, device=ev.device)
     check(lib().tef_events_to_channels_batched(ptr(ev), ptr(out), B, N, H, W, stream()), "tef_events_to_channels_batched")
     return out
+
+
+def get_hot_event_mask(event_rate, idx, max_px=100, min_obvs=5, max_rate=0.8):
+    """Binary mask that removes hot pixels.  **Not part of tudelft/taming_event_flow** (``BASELINE.json`` names it;
+    SURVEY.md §0) -- parity is unpinned.  Specification: the routine of the same name in tudelft/event_flow's
+    ``dataloader/encodings.py``: if ``idx > min_obvs``, up to ``max_px`` times take the arg-max of ``event_rate`` and, while it
+    exceeds ``max_rate``, zero it (in place, as there) and clear the mask there.  Returns the ``[H x W]`` mask of ones/zeros."""
+    require_cuda(event_rate)
+    if not (event_rate.is_contiguous() and event_rate.dtype == torch.float32 and event_rate.dim() == 2):
+        raise ValueError("event_rate must be a contiguous float32 [H, W] tensor (it is updated in place)")
+    H, W = event_rate.shape
+    mask = torch.empty_like(event_rate)
+    check(lib().tef_get_hot_event_mask(ptr(event_rate), ptr(mask), H, W, int(idx), int(max_px), int(min_obvs), ctypes.c_float(max_rate), stream()),
+          "tef_get_hot_event_mask")
+    return mask

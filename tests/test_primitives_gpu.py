@@ -172,3 +172,22 @@ def test_encodings_sizes(n):
     v = events_to_voxel(xs.cuda(), ys.cuda(), ts.cuda(), ps.cuda(), bins, (H, W)).cpu().numpy()
     ref = orc.events_to_voxel(xs.numpy(), ys.numpy(), ts.numpy(), ps.numpy(), bins, (H, W))
     assert rel_err(v, ref)[0] < TOL if n else not v.any()
+
+
+def test_get_hot_event_mask_against_its_specification():
+    """get_hot_event_mask is not in the reference (parity unpinned); the kernel is checked bit-exactly against
+    the CPU restatement of its published specification, including ties, the min_obvs gate and the max_px cap."""
+    from taming_event_flow_b200.dataloader.encodings import get_hot_event_mask
+
+    g = torch.Generator().manual_seed(4)
+    H, W = 60, 80
+    rate = torch.rand(H, W, generator=g) * 0.7
+    hot = torch.randperm(H * W, generator=g)[:150]
+    rate.view(-1)[hot] = 0.8 + torch.rand(150, generator=g)
+    rate.view(-1)[hot[:10]] = 1.25                                   # ties: the lowest flat index goes first
+    for idx, max_px in ((3, 100), (6, 100), (6, 1000), (6, 0)):
+        r = rate.clone().cuda()
+        m = get_hot_event_mask(r, idx, max_px=max_px)
+        em, er = orc.get_hot_event_mask(rate.numpy(), idx, max_px=max_px)
+        assert np.array_equal(m.cpu().numpy(), em) and np.array_equal(r.cpu().numpy(), er)
+        assert int((m == 0).sum()) == (0 if idx <= 5 else min(max_px, 150))
