@@ -59,6 +59,8 @@ def event_propagation(events_ts, events_idx, flow, tref):
     :param tref: reference time toward which events are warped
     :return: warped event locations [batch_size x N x 2]
     """
+    if not torch.is_tensor(events_ts):      # upstream also passes a plain number (loss/flow_val.py:57)
+        events_ts = torch.full(events_idx.shape[:-1] + (1,), float(events_ts), dtype=torch.float32, device=events_idx.device)
     require_cuda(events_ts, events_idx, flow)
     return _Propagate.apply(events_ts, events_idx, flow, float(tref))
 
@@ -129,9 +131,11 @@ class _Purge(torch.autograd.Function):
 def purge_unfeasible(event_loc, event_pol_mask, res):
     """Zero the location and polarity mask of events warped outside the image (upstream ``utils/iwe.py:43-60``)."""
     require_cuda(event_loc, event_pol_mask)
-    if event_pol_mask.shape != event_loc.shape:
+    cols = event_pol_mask.shape[-1]
+    if event_pol_mask.shape != event_loc.shape:       # e.g. a [B,N,1] mask (loss/flow_val.py:58): broadcast like upstream
         event_pol_mask = event_pol_mask.expand_as(event_loc)
-    return _Purge.apply(event_loc, event_pol_mask, int(res[0]), int(res[1]))
+    loc, mask = _Purge.apply(event_loc, event_pol_mask, int(res[0]), int(res[1]))
+    return loc, (mask if cols == mask.shape[-1] else mask[..., 0:cols])
 
 
 # --------------------------------------------------------------------------------------------

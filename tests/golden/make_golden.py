@@ -211,6 +211,48 @@ def make_encoding_cases():
     print("encoding cases written")
 
 
+def make_flow_val_cases():
+    """loss/flow_val.py (first "next" row of SURVEY.md §8f): Linear and Iterative validation on a synthetic 5-window sequence."""
+    from loss import flow_val as ref_val
+
+    H, W, P, N = 40, 56, 5, 1200
+    gen = torch.Generator().manual_seed(77)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
+    wins = []
+    for t in range(P):
+        ev, mk = syn.make_window(gen, 1, N, H, W)
+        flow = syn.make_flow(gen, 1, H, W, 2.0, coarse=8)
+        emask = (torch.rand(1, 1, H, W, generator=gen) > 0.3).float()
+        wins.append((ev, mk, flow, emask))
+    gt = syn.make_flow(gen, 1, H, W, 2.0, coarse=8)
+    gt[:, :, :5] = 0.0                                                    # pixels without ground truth
+    out = {"H": H, "W": W, "P": P, "gt": gt.numpy()}
+    for t, (ev, mk, flow, emask) in enumerate(wins):
+        out["ev%d" % t], out["mk%d" % t], out["flow%d" % t], out["emask%d" % t] = ev.numpy(), mk.numpy(), flow.numpy(), emask.numpy()
+    for name, cls in (("linear", ref_val.Linear), ("iterative", ref_val.Iterative)):
+        m = cls(copy.deepcopy(cfg), "cpu")
+        for t, (ev, mk, flow, emask) in enumerate(wins):
+            m.update([flow.clone()], ev.clone(), mk.clone(), emask.clone())
+            if t in (0, 2, P - 1):                                        # metrics after 1, 3 and 5 windows
+                key = "%s_t%d_" % (name, t)
+                out[key + "fwl"] = m.fwl().numpy()
+                out[key + "rsat"] = m.rsat().numpy()
+                out[key + "events"] = m.window_events().numpy()
+                out[key + "events_round"] = m.window_events(round_idx=True).numpy()
+                out[key + "aee"] = m.compute_aee(flow, gt, mask=m._event_mask).numpy()
+                modes = (None,) if name == "linear" else (None, "forward", "backward")
+                for mode in modes:
+                    out[key + "flow_%s" % mode] = m.window_flow(mode=mode).numpy()
+                    out[key + "flow_nomask_%s" % mode] = m.window_flow(mode=mode, mask=False).numpy()
+                for mode in ((None,) if name == "linear" else ("forward", "backward")):
+                    for ri in (False, True):
+                        out[key + "iwe_%s_%d" % (mode, ri)] = m.window_iwe(mode=mode, round_idx=ri).numpy()
+        m.reset()
+        assert m.num_passes == 0
+    np.savez_compressed(os.path.join(HERE, "flow_val.npz"), **out)
+    print("flow_val cases written")
+
+
 if __name__ == "__main__":
     import warnings
 
@@ -218,4 +260,5 @@ if __name__ == "__main__":
     make_loss_cases()
     make_primitive_cases()
     make_encoding_cases()
+    make_flow_val_cases()
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
