@@ -63,6 +63,11 @@ INFER_WORKLOADS = {
     "inference_480x640_500kev": dict(N=500_000, H=480, W=640, bins=5),
     "inference_480x640_1Mev": dict(N=1_000_000, H=480, W=640, bins=5),
 }
+# the validation criteria of loss/flow_val.py on the CUDA primitives (Iterative flavour, 10-window interval)
+VAL_WORKLOADS = {
+    "validation_480x640_100kev": dict(N=100_000, H=480, W=640, P=10),
+    "validation_480x640_500kev": dict(N=500_000, H=480, W=640, P=10),
+}
 DEFAULT_WORKLOAD = "iterative_480x640_1Mev"
 
 
@@ -657,14 +662,62 @@ def run_inference(args, wl):
                      "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "algorithmic_bytes_per_launch": nbytes}}))
 
 
+def run_validation(args, wl):
+    """eval_flow.py:114-176 without the network: per window `criteria.update(...)`, and FWL + RSAT every P windows."""
+    from taming_event_flow_b200 import synthetic as syn
+    from taming_event_flow_b200.loss import flow_val as fv
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    H, W, N, P = wl["H"], wl["W"], wl["N"], wl["P"]
+    g = torch.Generator().manual_seed(9)
+    wins = []
+    for t in range(P):
+        ev, mk = syn.make_window(g, 1, N, H, W)
+        wins.append((ev.to(dev), mk.to(dev), syn.make_flow(g, 1, H, W, 3.0).to(dev), torch.ones(1, 1, H, W, device=dev)))
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["FWL", "RSAT"]}}
+    crit = fv.Iterative(cfg, dev)
+
+    def interval():
+        crit.reset()
+        for ev, mk, flow, em in wins:
+            crit.update([flow], ev.clone(), mk, em)
+        return crit.fwl(), crit.rsat()
+
+    with torch.no_grad():
+        for _ in range(max(2, args.warmup // 2)):
+            interval()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            fwl, rsat = interval()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({
+        "metric": "validation_throughput", "value": P / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "events_per_window": N, "resolution": [H, W], "windows_per_interval": P,
+                   "criteria": "flow_val.Iterative update x P + FWL + RSAT"},
+        "fwl": float(fwl.item()), "rsat": float(rsat.item()), "Mevents_per_s": P * N / (ms * 1e-3) / 1e6}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + sorted(INFER_WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
+                    choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + sorted(INFER_WORKLOADS) + sorted(VAL_WORKLOADS))
     args = ap.parse_args()
+    if args.workload in VAL_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the CM-loss workloads only"}))
+            return
+        run_validation(args, dict(VAL_WORKLOADS[args.workload], name=args.workload))
+        return
     if args.workload in INFER_WORKLOADS:
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the CM-loss workloads only"}))
