@@ -45,6 +45,7 @@ WORKLOADS = {
     "iterative_480x640_250kev": dict(B=1, P=10, N=250_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
     "iterative_480x640_500kev": dict(B=1, P=10, N=500_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
     "iterative_480x640_2Mev": dict(B=1, P=10, N=2_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
+    "iterative_240x320_1Mev": dict(B=1, P=10, N=1_000_000, Nd=0, H=240, W=320, F=1, S=1, mode="two", sigma=1.5, dist="uniform", warping="Iterative"),
     "iterative_480x640_1Mev_edges": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="edges", warping="Iterative"),
     # BASELINE.json configs[0]: 128x128 crops, batch 8, 10 passes x (10k grad + 10k detached)
     "iterative_128x128_b8_f1": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),

@@ -66,7 +66,7 @@ struct CmParams {
     const float2 *flow;
     float2 *gflow;
     float2 *img;             // deterministic mode: same layout with every float replaced by an int64 (twice the bytes)
-    float2 *gimg;            // deterministic mode: gradient images [F][B][slot][pol][H][Wp] float2 (otherwise in place in img)
+    float2 *gimg;            // deterministic mode: gradient images [F][B][slot][phase][pol][H][Wp] float2 (otherwise in place in img)
     float2 *posbuf;          // [(P+1)][rows_grad] chain positions of the gradient-carrying rows (Iterative)
     uint32_t *alivebuf;      // [F][rows_grad] cumulative in-image bits (bit tref)
     long rows_grad;
@@ -78,12 +78,6 @@ struct CmParams {
     SegTable seg;
     ScaleTable sc;
     SortGeom sort;
-};
-
-// slot -> scale / divisor tables for the reduction kernels (few entries, in constant param space)
-struct SlotInfo {
-    int s;         // temporal scale index
-    float div_a;   // 2*delta+1 (Iterative, loss/flow.py:731) or 2 (Linear, :397)
 };
 
 inline int build_scales(const tef_cm_desc *d, int linear, ScaleTable &sc) {

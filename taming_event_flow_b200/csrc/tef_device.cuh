@@ -179,10 +179,7 @@ __device__ __forceinline__ float d1(float v, float c) {
     return (u > 0.0f) ? -sg : ((u == 0.0f) ? -0.5f * sg : 0.0f);
 }
 
-// native vector reduction: REDG.E.ADD.F32x2 on sm_100a (no return value requested)
-__device__ __forceinline__ void red_add_v2(float2 *addr, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
+// native fp32 reduction (REDG.E.ADD.F32, no return value requested); the 16-byte variant is in tef_cm_common.cuh
 __device__ __forceinline__ void red_add_f32(float *addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
