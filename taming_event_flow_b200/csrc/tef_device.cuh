@@ -39,21 +39,6 @@ __device__ __forceinline__ float div_const(float a, float c, float rc) {
     return a / c;
 }
 
-// two quotients with one (rarely taken) guard: the slow IEEE divisions sit in an out-of-line function
-static __device__ __noinline__ void div_const_slow(float a, float ca, float b, float cb, float &qa, float &qb) {
-    if (!(fabsf(a) >= 1e-30f)) qa = a / ca;
-    if (!(fabsf(b) >= 1e-30f)) qb = b / cb;
-}
-__device__ __forceinline__ void div_const2(float a, float ca, float rca, float b, float cb, float rcb, float &qa, float &qb) {
-    const float a0 = a * rca, b0 = b * rcb;
-    qa = __fmaf_rn(__fmaf_rn(-a0, ca, a), rca, a0);
-    qb = __fmaf_rn(__fmaf_rn(-b0, cb, b), rcb, b0);
-    if (!(fminf(fabsf(a), fabsf(b)) >= 1e-30f) && (a != 0.0f || b != 0.0f)) {
-        // a zero numerator gives an exact 0 on the fast path; only tiny non-zero numerators need the IEEE division
-        if ((a != 0.0f && !(fabsf(a) >= 1e-30f)) || (b != 0.0f && !(fabsf(b) >= 1e-30f))) div_const_slow(a, ca, b, cb, qa, qb);
-    }
-}
-
 // purge_unfeasible (utils/iwe.py:52-57): inclusive bounds [0, res-1]; (float)H - 1.0f == (float)(H-1) for any image size
 __device__ __forceinline__ bool inside(float y, float x, const Res &r) {
     return (y >= 0.0f) && (y <= r.hm1) && (x >= 0.0f) && (x <= r.wm1);
@@ -130,9 +115,8 @@ __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, co
 // Bit-identical to sample_flow() on such positions.
 template <bool KEEP>
 __device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
-    float qy, qx;
-    div_const2(2.0f * y, r.hm1, r.rhm1, 2.0f * x, r.wm1, r.rwm1, qy, qx);
-    const float gy = qy - 1.0f, gx = qx - 1.0f;
+    const float gy = div_const(2.0f * y, r.hm1, r.rhm1) - 1.0f;
+    const float gx = div_const(2.0f * x, r.wm1, r.rwm1) - 1.0f;
     const float iy = (gy + 1.0f) * r.sh, ix = (gx + 1.0f) * r.sw;
     const float fy0 = floorf(iy), fx0 = floorf(ix);
     const float w_ = ix - fx0, e_ = 1.0f - w_;
