@@ -116,7 +116,7 @@ extern "C" int tef_linear_backward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 1, p);
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
-    grad_segments_only(p);
+    grad_segments_only(p, (long)p.B * p.nslots * 4 * p.ig.plane * 8);
     if (p.det && !p.gimg) return TEF_EINVAL;
     cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * (p.det ? 4 : 2) * p.ig.plane, st);
     rc = tef_grad_images(p, st);
