@@ -14,8 +14,8 @@ struct SegTable {
     int nseg;
     int set[kMaxSeg], pass[kMaxSeg], n[kMaxSeg];
     int blk_off[kMaxSeg + 1];
-    int nbands, nchunks, grid_x;     // band-major CTA order of the event kernels (see build_bands / locate_sorted)
-    int *band_tab;                   // device: cta_start[nchunks + 1], row_lo[nchunks], row_hi[nchunks]
+    int nbands, band_ctas[kMaxSeg];  // band-major CTA order of the event kernels (see locate_sorted)
+    int band_off[33];
     const float4 *ev[kMaxSeg];
     const float2 *mk[kMaxSeg];
     int first_bin[kMaxSeg + 1];      // first sort bin of the segment (bins are segment-major)
@@ -109,24 +109,29 @@ inline int check_desc(const tef_cm_desc *d, int linear) {
     return 0;
 }
 
-// Band-major CTA order.  Every segment is tile-sorted (tiles row-major over the image), so tiles [k*T/K, (k+1)*T/K) of
-// every segment cover the same horizontal stripe of the image.  The event kernels run stripe k of ALL segments (and then
-// of the next sample) before stripe k+1 of any, which keeps the slot images, gradient images and flow-gradient maps of
-// that stripe in L2 while every pass that touches it goes by (the segment-after-segment order re-fetched each image
-// ~8 times: profiles/r1_g, 3.2 GB of DRAM traffic in the forward kernel, 1.45 GB afterwards).
-// chunk c = (stripe k, sample b, segment s); its rows come from the sort bins, so the CTA table is built on the device
-// (band_table_kernel) and the kernels are launched with an upper bound of CTAs.
+// Band-major CTA order.  Every segment is tile-sorted, so the k-th fraction of each segment covers about the same
+// image region.  Running band k of ALL segments before band k+1 of any keeps the slot images, gradient images and
+// flow-gradient maps of that region in L2 while every pass that touches it goes by (the segment-after-segment
+// order re-fetched each image ~8 times: profiles/r1_g, 3.2 GB of DRAM traffic in the forward kernel).
 inline void build_bands(CmParams &p, long image_bytes) {
     SegTable &g = p.seg;
     int nb = (int)(image_bytes / (4l << 20));
-    nb = nb < 1 ? 1 : (nb > 32 ? 32 : nb);
-    if (nb > p.sort.tiles) nb = p.sort.tiles;
-    g.nbands = nb;
-    g.nchunks = nb * p.B * g.nseg;
-    g.grid_x = g.blk_off[g.nseg] + g.nchunks;             // every chunk rounds its rows up to whole CTAs
-    g.band_tab = p.sort.sums + (p.sort.nbins / 2048 + 2);
+    g.nbands = nb < 1 ? 1 : (nb > 32 ? 32 : nb);
+    for (int s = 0; s < g.nseg; ++s) {
+        const int c = g.blk_off[s + 1] - g.blk_off[s];
+        g.band_ctas[s] = (c + g.nbands - 1) / g.nbands;
+    }
+    g.band_off[0] = 0;
+    for (int k = 0; k < g.nbands; ++k) {
+        int n = 0;
+        for (int s = 0; s < g.nseg; ++s) {
+            const int c = g.blk_off[s + 1] - g.blk_off[s];
+            const int left = c - k * g.band_ctas[s];
+            n += left < 0 ? 0 : (left > g.band_ctas[s] ? g.band_ctas[s] : left);
+        }
+        g.band_off[k + 1] = g.band_off[k] + n;
+    }
 }
-inline long band_tab_ints(const CmParams &p) { return 3l * p.seg.nchunks + 4; }
 
 inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     int rc = check_desc(d, linear);
@@ -170,7 +175,12 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
 }
 
 // the backward only visits the gradient-carrying set; its segments come first
-
+inline void grad_segments_only(CmParams &p, long image_bytes) {
+    int ng = 0;
+    while (ng < p.seg.nseg && p.seg.set[ng] == 0) ++ng;
+    p.seg.nseg = ng;
+    build_bands(p, image_bytes);
+}
 
 // rows of segment sg in the sorted arrays: [lo, hi)
 __device__ __forceinline__ void seg_rows(const CmParams &p, int sg, int &lo, int &hi) {
@@ -181,17 +191,22 @@ __device__ __forceinline__ void seg_rows(const CmParams &p, int sg, int &lo, int
 
 // CTA -> segment, thread -> sorted row; false when the thread has no event
 __device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b, float4 &e, float2 &m, int &row, int &set) {
-    // blockIdx.x -> chunk (stripe, sample, segment) by binary search in the device-built CTA table; uniform per CTA
-    const int *tab = p.seg.band_tab;
-    const int nch = p.seg.nchunks, blk = blockIdx.x;
-    t = 0; set = 1; row = 0;
-    if (blk >= __ldg(tab + nch)) return false;             // beyond the CTAs actually needed
-    int c0 = 0, c1 = nch;                                  // largest c with cta_start[c] <= blk
-    while (c1 - c0 > 1) { const int mid = (c0 + c1) >> 1; if (__ldg(tab + mid) <= blk) c0 = mid; else c1 = mid; }
-    const int sg = c0 % p.seg.nseg;
+    // blockIdx.x -> (band, segment, CTA inside the segment); all of it uniform per CTA
+    int k = 0;
+    while ((int)blockIdx.x >= p.seg.band_off[k + 1]) ++k;
+    int rem = blockIdx.x - p.seg.band_off[k], sg = 0, cta = 0;
+    for (;; ++sg) {
+        const int c = p.seg.blk_off[sg + 1] - p.seg.blk_off[sg];
+        const int left = c - k * p.seg.band_ctas[sg];
+        const int n = left < 0 ? 0 : min(left, p.seg.band_ctas[sg]);
+        if (rem < n) { cta = k * p.seg.band_ctas[sg] + rem; break; }
+        rem -= n;
+    }
     t = p.seg.pass[sg]; set = p.seg.set[sg];
-    row = __ldg(tab + nch + 1 + c0) + (blk - __ldg(tab + c0)) * kThreads + threadIdx.x;
-    if (row >= __ldg(tab + 2 * nch + 1 + c0)) return false;
+    int lo, hi;
+    seg_rows(p, sg, lo, hi);
+    row = lo + cta * kThreads + threadIdx.x;
+    if (row >= hi) return false;
     float m2, m3;
     // one 256-bit load per event (LDG.E.ENL2.256): the whole 32-byte sorted record
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

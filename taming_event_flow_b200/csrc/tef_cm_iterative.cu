@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     __shared__ WinS sw[TEF_MAX_SCALES];
     int t, b, row, set; float4 e; float2 m;
     const bool live = locate_sorted(p, t, b, e, m, row, set);
-    if (set != 0) return;                                          // detached events carry no gradient (uniform per CTA)
     build_windows(p, t, sw);
     if (!live) return;
     const int f = blockIdx.y;
@@ -273,7 +272,7 @@ static int launch_fwd(const CmParams &p, cudaStream_t st) {
             cudaFuncSetAttribute(iter_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             attr = true;
         }
-        dim3 grid(p.seg.grid_x, p.F);
+        dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_FWD, st);
         if (p.det) iter_fwd_kernel<true><<<grid, kThreads, chain_smem(p), st>>>(p);
         else iter_fwd_kernel<false><<<grid, kThreads, chain_smem(p), st>>>(p);
@@ -282,7 +281,7 @@ static int launch_fwd(const CmParams &p, cudaStream_t st) {
 }
 static int launch_bwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
-        dim3 grid(p.seg.grid_x, p.F);
+        dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_BWD, st);
         if (p.det) iter_bwd_kernel<true><<<grid, kThreads, 0, st>>>(p);
         else iter_bwd_kernel<false><<<grid, kThreads, 0, st>>>(p);
@@ -312,6 +311,7 @@ extern "C" int tef_iterative_backward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
     if (p.rows_grad > 0 && (!p.posbuf || !p.alivebuf)) return TEF_EINVAL;
+    grad_segments_only(p, (long)p.B * p.nslots * 4 * p.ig.plane * 8);
     if (p.det && !p.gimg) return TEF_EINVAL;
     cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * (p.det ? 4 : 2) * p.ig.plane, st);
     rc = tef_grad_images(p, st);

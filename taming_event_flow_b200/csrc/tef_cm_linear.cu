@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
 template <bool DET>
 __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
-    if (!locate_sorted(p, t, b, e, m, row, set) || set != 0) return;
+    if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
     const long HW = (long)p.H * p.W;
     const long mo = (((long)f * p.P + t) * p.B + b) * 2 * p.res.fplane;
@@ -102,8 +102,8 @@ extern "C" int tef_linear_forward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         ProfScope ps(K_LIN_FWD, st);
-        if (p.det) linear_fwd_kernel<true><<<dim3(p.seg.grid_x, p.F), kThreads, 0, st>>>(p);
-        else linear_fwd_kernel<false><<<dim3(p.seg.grid_x, p.F), kThreads, 0, st>>>(p);
+        if (p.det) linear_fwd_kernel<true><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        else linear_fwd_kernel<false><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
     }
     rc = (int)cudaGetLastError();
     if (rc) return rc;
@@ -116,14 +116,15 @@ extern "C" int tef_linear_backward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 1, p);
     if (rc) return rc;
     if (!p.flow || !p.gflow || !p.img || !p.den || !p.grad_out || !p.sort.bins || !p.sort.rec) return TEF_EINVAL;
+    grad_segments_only(p, (long)p.B * p.nslots * 4 * p.ig.plane * 8);
     if (p.det && !p.gimg) return TEF_EINVAL;
     cudaMemsetAsync(p.gflow, 0, sizeof(float2) * (long)p.F * p.P * p.B * (p.det ? 4 : 2) * p.ig.plane, st);
     rc = tef_grad_images(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         ProfScope ps(K_LIN_BWD, st);
-        if (p.det) linear_bwd_kernel<true><<<dim3(p.seg.grid_x, p.F), kThreads, 0, st>>>(p);
-        else linear_bwd_kernel<false><<<dim3(p.seg.grid_x, p.F), kThreads, 0, st>>>(p);
+        if (p.det) linear_bwd_kernel<true><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
+        else linear_bwd_kernel<false><<<dim3(p.seg.blk_off[p.seg.nseg], p.F), kThreads, 0, st>>>(p);
     }
     return (int)cudaGetLastError();
 }

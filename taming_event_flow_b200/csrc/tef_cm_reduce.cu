@@ -174,7 +174,7 @@ extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 * wide;   // floats in img
     out[2] = (long)p.F * p.P * p.B * 2 * p.ig.plane * 2 * wide;        // floats in gflow
     out[3] = p.sort.nbins + 1;                                    // ints in sort_bins
-    out[4] = p.sort.nbins / 2048 + 2 + band_tab_ints(p);          // ints in sort_sums (scan scratch + band-order CTA table)
+    out[4] = p.sort.nbins / 2048 + 2;                             // ints in sort_sums
     out[5] = r;                                                   // rows of sorted_ev / sorted_mk
     out[6] = p.rows_grad;                                         // gradient-carrying rows
     out[7] = linear ? 0 : (long)p.F * (p.P + 1) * p.rows_grad * 2; // floats in posbuf (alivebuf: F * rows_grad u64)

@@ -141,32 +141,6 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(int *__restrict__ 
     for (int k = 0; k < 8; ++k) { if (base + k < nbins) bins[base + k] = run; run += v[k]; }
 }
 
-// CTA table of the band-major order (tef_cm_common.cuh: build_bands): one CTA; rows of chunk (k, b, s) from the bin ends,
-// CTAs per chunk, exclusive prefix.
-__global__ void __launch_bounds__(kThreads) band_table_kernel(const __grid_constant__ CmParams p) {
-    const int nch = p.seg.nchunks, K = p.seg.nbands, T = p.sort.tiles, nseg = p.seg.nseg;
-    int *tab = p.seg.band_tab;
-    int carry = 0;
-    for (int base = 0; base < nch; base += kThreads) {
-        const int c = base + threadIdx.x;
-        int ctas = 0;
-        if (c < nch) {
-            const int s = c % nseg, b = (c / nseg) % p.B, k = c / (nseg * p.B);
-            const long t0 = (long)k * T / K, t1 = (long)(k + 1) * T / K;
-            const long first = (((long)s * p.B + b) * T + t0) * 128, last = (((long)s * p.B + b) * T + t1) * 128;
-            const int lo = first ? p.sort.bins[first - 1] : 0;
-            const int hi = last ? p.sort.bins[last - 1] : 0;
-            tab[nch + 1 + c] = lo; tab[2 * nch + 1 + c] = hi;
-            ctas = (hi - lo + kThreads - 1) / kThreads;
-        }
-        int total;
-        const int ex = block_exclusive_scan(ctas, &total);
-        if (c < nch) tab[c] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) tab[nch] = carry;
-}
-
 }  // namespace tef
 
 using namespace tef;
@@ -185,6 +159,5 @@ int tef_sort_events(const CmParams &p, cudaStream_t st) {
     { ProfScope ps(K_SORT_SCAN, st); scan_top_kernel<<<1, kThreads, 0, st>>>(p.sort.sums, nchunks); }
     { ProfScope ps(K_SORT_SCAN, st); scan_apply_kernel<<<nchunks, kThreads, 0, st>>>(p.sort.bins, p.sort.sums, nbins); }
     { ProfScope ps(K_SORT_SCATTER, st); sort_scatter_kernel<<<nblk, kThreads, 0, st>>>(p); }
-    { ProfScope ps(K_SORT_SCAN, st); band_table_kernel<<<1, kThreads, 0, st>>>(p); }
     return (int)cudaGetLastError();
 }
