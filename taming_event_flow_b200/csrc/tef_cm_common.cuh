@@ -1,5 +1,6 @@
 // tef_cm_common.cuh -- host/device tables shared by the fused CM-loss kernels.
 #pragma once
+#include <cstdlib>
 #include "tef_device.cuh"
 #include "../../include/tef_b200.h"
 
@@ -115,7 +116,12 @@ inline int check_desc(const tef_cm_desc *d, int linear) {
 // order re-fetched each image ~8 times: profiles/r1_g, 3.2 GB of DRAM traffic in the forward kernel).
 inline void build_bands(CmParams &p, long image_bytes) {
     SegTable &g = p.seg;
-    int nb = (int)(image_bytes / (4l << 20));
+    static const long target = [] {                      // tuning knob; 8 MB per band measured best on B200 (profiles/r1_band_sweep.txt)
+        const char *e = getenv("TEF_BAND_BYTES");
+        const long v = e ? atol(e) : 0;
+        return v > 0 ? v : (8l << 20);
+    }();
+    int nb = (int)(image_bytes / target);
     g.nbands = nb < 1 ? 1 : (nb > 32 ? 32 : nb);
     for (int s = 0; s < g.nseg; ++s) {
         const int c = g.blk_off[s + 1] - g.blk_off[s];
@@ -207,7 +213,7 @@ __device__ __forceinline__ bool locate_sorted(const CmParams &p, int &t, int &b,
     seg_rows(p, sg, lo, hi);
     row = lo + cta * kThreads + threadIdx.x;
     if (row >= hi) return false;
-    float m2, m3;
+    __attribute__((unused)) float m2, m3;            // record padding
     // one 256-bit load per event (LDG.E.ENL2.256): the whole 32-byte sorted record
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w), "=f"(m.x), "=f"(m.y), "=f"(m2), "=f"(m3)

@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
-    const long HW = (long)p.H * p.W;
     const float2 vxy = sample_flow<false>(p.flow + (((long)f * p.P + t) * p.B + b) * 2 * p.res.fplane, p.res, e.y, e.z, nullptr);
     const float2 v = make_float2(vxy.y, vxy.x);                        // (y, x), utils/iwe.py:38
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;
@@ -55,7 +54,6 @@ __global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_const
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;
-    const long HW = (long)p.H * p.W;
     const long mo = (((long)f * p.P + t) * p.B + b) * 2 * p.res.fplane;
     Taps tp;
     const float2 vxy = sample_flow<true>(p.flow + mo, p.res, e.y, e.z, &tp);
