@@ -162,6 +162,28 @@ int tef_get_hot_event_mask(float *event_rate, float *mask, int H, int W, int idx
 /* events_to_voxel (:32-56): out [bins][H][W] */
 int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* dataloader/base.py -- the loader -> loss contract          */
+/* ------------------------------------------------------------------------- */
+/* create_polarity_mask (:264-278): ps [n] -> mask [2][n] */
+int tef_create_polarity_mask(const float *ps, float *mask, long n, void *stream);
+/* create_mask_encoding (:302-314): cnt [B][2][H][W] -> out [B][1][H][W] */
+int tef_create_mask_encoding(const float *cnt, float *out, int B, int H, int W, void *stream);
+/* custom_collate (:391-434) for one sample: src [C][n] -> dst rows [N][C], zero rows n..N (the caller offsets dst per sample) */
+int tef_collate_events(const float *src, float *dst, long n, long N, int C, void *stream);
+/* event_formatting (:139-170) + create_list_encoding (:247-262) + create_polarity_mask + custom_collate for a ragged batch
+   that crossed PCIe as 8-byte packed events {fp32 raw ts, x | y << 14 | pol << 28}: window b = packed[offsets[b] : offsets[b+1]]
+   (offsets: B+1 longs in device memory).  Writes event_list [B][n_pad][4] = (ts normalised, y, x, p = pol*2-1), pol_mask
+   [B][n_pad][2], zero rows as padding and, when cnt is not NULL, events_to_channels of every window: cnt [B][2][H][W] */
+int tef_format_events(const void *packed, const long *offsets, int B, long n_pad, float *event_list, float *pol_mask,
+                      float *cnt, int H, int W, void *stream);
+/* split_event_list (:347-377) on the padded batch: every sample's events are ranked by a keyed pseudo-random permutation
+   (Feistel network, cycle-walked; `seed` picks it); rank < k -> gradient list [B][Ng] at row rank, else detached list
+   [B][Nd] at row rank-k; samples with at most k events keep their order and detach nothing.  Outputs are zeroed inside
+   (padding rows). */
+int tef_split_events(const float *event_list, const float *pol_mask, const long *offsets, unsigned long long seed, int B, long N, long k,
+                     float *g_events, float *g_mask, long Ng, float *d_events, float *d_mask, long Nd, void *stream);
+
 /* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers;
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */
 int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream);

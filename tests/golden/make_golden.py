@@ -253,6 +253,42 @@ def make_flow_val_cases():
     print("flow_val cases written")
 
 
+def make_loader_cases():
+    """dataloader/base.py: the static methods of the UNMODIFIED BaseDataLoader on three ragged windows."""
+    import types
+
+    from dataloader.base import BaseDataLoader  # noqa: E402  (reference)
+
+    rng = np.random.default_rng(11)
+    H, W = 40, 56
+    me = types.SimpleNamespace(device=torch.device("cpu"))
+    out = {"H": H, "W": W, "counts": np.array([700, 1, 0, 1200])}
+    batch = []
+    for b, n in enumerate(out["counts"]):
+        xs = rng.integers(0, W, n).astype(np.int64)
+        ys = rng.integers(0, H, n).astype(np.int64)
+        ts = np.sort(rng.uniform(2.0e5, 2.5e5, n))                          # raw float64 timestamps (us since file start)
+        ps = rng.integers(0, 2, n).astype(np.int64)
+        out.update({"xs%d" % b: xs, "ys%d" % b: ys, "ts%d" % b: ts, "ps%d" % b: ps})
+        fx, fy, ft, fp = BaseDataLoader.event_formatting(me, xs, ys, ts, ps)
+        ev = BaseDataLoader.create_list_encoding(fx, fy, ft, fp)
+        mk = BaseDataLoader.create_polarity_mask(fp)
+        cnt = ref_enc.events_to_channels(fx, fy, fp, sensor_size=(H, W))
+        out.update({"fmt_ts%d" % b: ft.numpy(), "fmt_ps%d" % b: fp.numpy(), "list%d" % b: ev.numpy(), "mask%d" % b: mk.numpy(),
+                    "cnt%d" % b: cnt.numpy(), "emask%d" % b: BaseDataLoader.create_mask_encoding(cnt).numpy()})
+        batch.append({"event_list": ev, "event_list_pol_mask": mk, "event_cnt": cnt, "d_event_list": torch.zeros((4, 0)),
+                      "d_event_list_pol_mask": torch.zeros((2, 0))})
+    col = BaseDataLoader.custom_collate(batch)
+    for k, v in col.items():
+        out["collate_" + k] = v.numpy()
+    # split_event_list: random; stored to document shapes and the partition property
+    torch.manual_seed(3)
+    g, gm, d, dm = BaseDataLoader.split_event_list(batch[3]["event_list"], batch[3]["event_list_pol_mask"], 500)
+    out.update({"split_g": g.numpy(), "split_gm": gm.numpy(), "split_d": d.numpy(), "split_dm": dm.numpy()})
+    np.savez_compressed(os.path.join(HERE, "loader.npz"), **out)
+    print("loader cases written")
+
+
 if __name__ == "__main__":
     import warnings
 
@@ -261,4 +297,5 @@ if __name__ == "__main__":
     make_primitive_cases()
     make_encoding_cases()
     make_flow_val_cases()
+    make_loader_cases()
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
