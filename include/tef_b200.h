@@ -184,6 +184,28 @@ int tef_format_events(const void *packed, const long *offsets, int B, long n_pad
 int tef_split_events(const float *event_list, const float *pol_mask, const long *offsets, unsigned long long seed, int B, long N, long k,
                      float *g_events, float *g_mask, long Ng, float *d_events, float *d_mask, long Nd, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* loss/flow_val.py -- fused stages of the validation update; */
+/* batch size 1 like upstream; maps are planar [H][W] (x and y flow separately) */
+/* ------------------------------------------------------------------------- */
+/* Iterative.update :483-517: every accumulated event one window forward with the newest map, in place:
+   loc [n][2] (y, x), ts [n] (set to tref), mask [n][2] */
+int tef_val_forward_step(const float *mapx, const float *mapy, float *loc, float *ts, float *mask, float tref, long n, int H, int W,
+                         void *stream);
+/* Iterative.update :519-556: the new window back to time 0 through maps n_maps-1 .. 0 (mapsx/mapsy [n_maps][H][W]); loc and
+   mask in place, ts [n] = the window's timestamps (read only) */
+int tef_val_backward_chain(const float *mapsx, const float *mapsy, int n_maps, float *loc, const float *ts, float *mask, long n,
+                           int H, int W, void *stream);
+/* forward_prop_flow :43-74 for n_maps consecutive maps (the i-th has time index first+i): each is carried to time first+i+1
+   (tref_is_next) or to `tref` by splatting it along itself.  acc: scratch [n_maps][3][H][W] (zeroed inside); outx/outy
+   [n_maps][H][W] may alias the inputs */
+int tef_val_forward_prop_flow(const float *mapsx, const float *mapsy, int first, int n_maps, int tref_is_next, float tref, float *acc,
+                              float *outx, float *outy, int H, int W, void *stream);
+/* Iterative.update :579-605: pixel trajectories through the newest map: idx [2][H][W] (y, x planes) and out_mask [H][W] in
+   place, accx/accy [H][W] = accumulated displacement */
+int tef_val_trajectory_step(const float *mapx, const float *mapy, float *idx, float *out_mask, float *accx, float *accy, int H, int W,
+                            void *stream);
+
 /* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers;
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */
 int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream);

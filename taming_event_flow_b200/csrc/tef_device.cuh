@@ -145,6 +145,24 @@ __device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ 
     return make_float2(ox, oy);
 }
 
+// get_event_flow (utils/iwe.py:17-40) of one location (y, x) on planar maps [H][W]: ATen's bilinear grid_sample
+// arithmetic (nw*w0, then three FMAs), zero padding; returns (flow_y, flow_x) like utils/iwe.py:38
+__device__ __forceinline__ float2 event_flow_planar(const float *__restrict__ mapx, const float *__restrict__ mapy, float y, float x, const Res &r) {
+    Bil bl;
+    bilinear_setup(r, y, x, bl);
+    const long base = (long)bl.y0 * r.W + bl.x0;
+    const int off[4] = { 0, 1, r.W, r.W + 1 };
+    float ox = 0.f, oy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float vx = bl.ok[k] ? __ldg(mapx + base + off[k]) : 0.f;
+        const float vy = bl.ok[k] ? __ldg(mapy + base + off[k]) : 0.f;
+        if (k == 0) { ox = vx * bl.w[0]; oy = vy * bl.w[0]; }
+        else { ox = __fmaf_rn(vx, bl.w[k], ox); oy = __fmaf_rn(vy, bl.w[k], oy); }
+    }
+    return make_float2(oy, ox);
+}
+
 // get_interpolation, bilinear branch (utils/iwe.py:85-107), one event
 struct Corners {
     float cy[2], cx[2];   // top/bottom, left/right corner coordinates (as fp32)

@@ -38,19 +38,7 @@ __global__ void __launch_bounds__(kThreads) gef_fwd_kernel(const float *__restri
     const long HW = (long)r.H * r.W;
     const int b = (int)(i / N);
     const float2 l = loc[i];
-    Bil bl;
-    bilinear_setup(r, l.x, l.y, bl);
-    const long base = b * HW + (long)bl.y0 * r.W + bl.x0;
-    const int off[4] = { 0, 1, r.W, r.W + 1 };
-    float ox = 0.f, oy = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float vx = bl.ok[k] ? __ldg(mapx + base + off[k]) : 0.f;
-        const float vy = bl.ok[k] ? __ldg(mapy + base + off[k]) : 0.f;
-        if (k == 0) { ox = vx * bl.w[0]; oy = vy * bl.w[0]; }
-        else { ox = __fmaf_rn(vx, bl.w[k], ox); oy = __fmaf_rn(vy, bl.w[k], oy); }
-    }
-    out[i] = make_float2(oy, ox);      // (y, x) order, utils/iwe.py:38
+    out[i] = event_flow_planar(mapx + b * HW, mapy + b * HW, l.x, l.y, r);
 }
 __global__ void __launch_bounds__(kThreads) gef_bwd_kernel(const float2 *__restrict__ gout, const float *__restrict__ mapx,
                                                            const float *__restrict__ mapy, const float2 *__restrict__ loc,

@@ -1,0 +1,155 @@
+// tef_validation.cu -- fused steps of the reference's validation criteria (loss/flow_val.py).
+//
+// `Iterative.update` of the reference re-warps every accumulated event, pulls the new window back through every flow
+// map, and carries every older flow map one window forward by splatting it along itself: ~150 small eager ops per
+// window at ten windows, all launch-bound.  The four kernels below do one whole stage each, with the per-element
+// arithmetic of the stand-alone operators (tef_primitives.cu) in the same order, so results are bit-identical to the
+// operator-by-operator route except for the order of the image sums of the flow splat.  Validation runs with batch
+// size 1 like upstream (loss/flow_val.py:30-38 builds batch-1 index grids).
+#include "tef_cm_common.cuh"
+#include "tef_prof.cuh"
+
+namespace tef {
+
+// event_propagation + purge_unfeasible of one event (utils/iwe.py:5-14, :43-60)
+__device__ __forceinline__ float step_event(float2 &loc, float ts, float tref, float2 flow, const Res &r) {
+    const float dt = tref - ts;
+    const float y = loc.x + dt * flow.x, x = loc.y + dt * flow.y;
+    const float in = inside(y, x, r) ? 1.0f : 0.0f;
+    loc = make_float2(y * in, x * in);
+    return in;
+}
+
+// loss/flow_val.py:483-517: every event seen so far, one window forward with the newest flow map, in place
+__global__ void __launch_bounds__(kThreads) val_fw_step_kernel(const float *__restrict__ mapx, const float *__restrict__ mapy, float2 *__restrict__ loc,
+                                                               float *__restrict__ ts, float2 *__restrict__ mask, float tref, long n, Res r) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float2 l = loc[i];
+    const float2 m = mask[i];
+    const float in = step_event(l, ts[i], tref, event_flow_planar(mapx, mapy, l.x, l.y, r), r);
+    loc[i] = l;
+    mask[i] = make_float2(m.x * in, m.y * in);
+    ts[i] = tref;
+}
+
+// loss/flow_val.py:519-556: the new window back to time 0 through maps n_maps-1 ... 0 (maps [n_maps][H][W]), in place
+__global__ void __launch_bounds__(kThreads) val_bw_chain_kernel(const float *__restrict__ mapsx, const float *__restrict__ mapsy, int n_maps,
+                                                                float2 *__restrict__ loc, const float *__restrict__ ts0, float2 *__restrict__ mask,
+                                                                long n, Res r) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const long HW = (long)r.H * r.W;
+    float2 l = loc[i], m = mask[i];
+    float ts = ts0[i];
+    for (int k = n_maps - 1; k >= 0; --k) {
+        const float in = step_event(l, ts, (float)k, event_flow_planar(mapsx + k * HW, mapsy + k * HW, l.x, l.y, r), r);
+        m = make_float2(m.x * in, m.y * in);
+        ts = (float)k;
+    }
+    loc[i] = l;
+    mask[i] = m;
+}
+
+// forward_prop_flow (loss/flow_val.py:43-74), splat half: pixel p of map i moves by dt_i * flow and deposits
+// (weight, weight*flow_y, weight*flow_x) on its four corners; acc [n_maps][3][H][W]
+__global__ void __launch_bounds__(kThreads) val_prop_splat_kernel(const float *__restrict__ mapsx, const float *__restrict__ mapsy, int first, int n_maps,
+                                                                  int tref_is_next, float tref, float *__restrict__ acc, Res r) {
+    const long HW = (long)r.H * r.W;
+    const long j = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= HW * n_maps) return;
+    const int i = (int)(j / HW);
+    const long p = j - (long)i * HW;
+    const float py = (float)(p / r.W), px = (float)(p % r.W);
+    const float2 f = event_flow_planar(mapsx + i * HW, mapsy + i * HW, py, px, r);          // (y, x)
+    float2 l = make_float2(py, px);
+    const float in = step_event(l, (float)(first + i), tref_is_next ? (float)(first + i + 1) : tref, f, r);
+    Corners c;
+    corners(l.x, l.y, r, c);
+    float *a = acc + (long)i * 3 * HW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ky = k >> 1, kx = k & 1;
+        const float ok = (c.oky[ky] && c.okx[kx]) ? 1.0f : 0.0f;
+        const long id = (long)((c.cy[ky] * ok) * (float)r.W + c.cx[kx] * ok);               // utils/iwe.py:104,:110-111
+        const float w = (c.wy[ky] * c.wx[kx]) * ok;                                         // :107
+        const float vn = w * in, vy = (w * f.x) * in, vx = (w * f.y) * in;                  // interpolate(): weights * mask
+        if (vn != 0.0f) red_add_f32(a + id, vn);
+        if (vy != 0.0f) red_add_f32(a + HW + id, vy);
+        if (vx != 0.0f) red_add_f32(a + 2 * HW + id, vx);
+    }
+}
+// ... and the normalisation half: map = splat / (norm + 1e-9)
+__global__ void __launch_bounds__(kThreads) val_prop_norm_kernel(const float *__restrict__ acc, float *__restrict__ outx, float *__restrict__ outy,
+                                                                 int n_maps, long HW) {
+    const long j = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= HW * n_maps) return;
+    const long i = j / HW, p = j - i * HW;
+    const float *a = acc + i * 3 * HW;
+    const float d = a[p] + 1e-9f;
+    outy[j] = a[HW + p] / d;
+    outx[j] = a[2 * HW + p] / d;
+}
+
+// loss/flow_val.py:579-605: pixel trajectories through the newest map; idx [2][H][W] = (y, x) planes, in place
+__global__ void __launch_bounds__(kThreads) val_trajectory_kernel(const float *__restrict__ mapx, const float *__restrict__ mapy, float *__restrict__ idx,
+                                                                  float *__restrict__ out_mask, float *__restrict__ accx, float *__restrict__ accy, Res r) {
+    const long HW = (long)r.H * r.W;
+    const long p = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= HW) return;
+    const float y = idx[p], x = idx[HW + p];
+    const float valid = (y >= 0.0f && y <= r.hm1 && x >= 0.0f && x <= r.wm1) ? 1.0f : 0.0f;
+    out_mask[p] = out_mask[p] + valid;
+    const float2 f = event_flow_planar(mapx, mapy, y, x, r);
+    const float ny = y + f.x * valid, nx = x + f.y * valid;
+    idx[p] = ny; idx[HW + p] = nx;
+    accx[p] = nx - (float)(p % r.W);
+    accy[p] = ny - (float)(p / r.W);
+}
+
+}  // namespace tef
+
+using namespace tef;
+#define ST ((cudaStream_t)stream)
+#define TEF_GRID(n) (unsigned)(((n) + kThreads - 1) / kThreads)
+
+extern "C" int tef_val_forward_step(const float *mapx, const float *mapy, float *loc, float *ts, float *mask, float tref, long n, int H, int W,
+                                    void *stream) {
+    if (n < 0 || H < 2 || W < 2) return TEF_EINVAL;
+    if (n == 0) return 0;
+    if (!mapx || !mapy || !loc || !ts || !mask) return TEF_EINVAL;
+    ProfScope pr(K_VALIDATION, ST);
+    val_fw_step_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(mapx, mapy, (float2 *)loc, ts, (float2 *)mask, tref, n, Res::make(H, W));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_val_backward_chain(const float *mapsx, const float *mapsy, int n_maps, float *loc, const float *ts, float *mask, long n,
+                                      int H, int W, void *stream) {
+    if (n < 0 || n_maps < 1 || H < 2 || W < 2) return TEF_EINVAL;
+    if (n == 0) return 0;
+    if (!mapsx || !mapsy || !loc || !ts || !mask) return TEF_EINVAL;
+    ProfScope pr(K_VALIDATION, ST);
+    val_bw_chain_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>(mapsx, mapsy, n_maps, (float2 *)loc, ts, (float2 *)mask, n, Res::make(H, W));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_val_forward_prop_flow(const float *mapsx, const float *mapsy, int first, int n_maps, int tref_is_next, float tref, float *acc,
+                                         float *outx, float *outy, int H, int W, void *stream) {
+    if (first < 0 || n_maps < 0 || H < 2 || W < 2) return TEF_EINVAL;
+    if (n_maps == 0) return 0;
+    if (!mapsx || !mapsy || !acc || !outx || !outy) return TEF_EINVAL;
+    const long HW = (long)H * W;
+    cudaMemsetAsync(acc, 0, sizeof(float) * 3 * HW * n_maps, ST);
+    ProfScope pr(K_VALIDATION, ST);
+    val_prop_splat_kernel<<<TEF_GRID(HW * n_maps), kThreads, 0, ST>>>(mapsx, mapsy, first, n_maps, tref_is_next, tref, acc, Res::make(H, W));
+    val_prop_norm_kernel<<<TEF_GRID(HW * n_maps), kThreads, 0, ST>>>(acc, outx, outy, n_maps, HW);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_val_trajectory_step(const float *mapx, const float *mapy, float *idx, float *out_mask, float *accx, float *accy, int H, int W,
+                                       void *stream) {
+    if (H < 2 || W < 2 || !mapx || !mapy || !idx || !out_mask || !accx || !accy) return TEF_EINVAL;
+    ProfScope pr(K_VALIDATION, ST);
+    val_trajectory_kernel<<<TEF_GRID((long)H * W), kThreads, 0, ST>>>(mapx, mapy, idx, out_mask, accx, accy, Res::make(H, W));
+    return (int)cudaGetLastError();
+}

@@ -2,14 +2,23 @@
 
 Same classes and methods as upstream (``loss/flow_val.py:12-694``: ``BaseValidation``, ``Linear``, ``Iterative`` with
 ``update`` / ``reset`` / ``window_events`` / ``window_flow`` / ``window_iwe`` / ``rsat`` / ``fwl`` / ``compute_aee``).
-This is the first "next" row of SURVEY.md §8f: evaluation only, no gradients.  Every gather, warp, purge, index/weight and
-scatter step runs through the CUDA primitives of ``taming_event_flow_b200.utils.iwe`` (one kernel each); only the
-book-keeping around them (concatenating windows, averaging, variances) is left to torch.  It is pinned by golden vectors
-made from the unmodified reference (``tests/golden/make_golden.py``), not by the C oracle.
+This is the first "next" row of SURVEY.md §8f: evaluation only, no gradients.  The stages of ``Iterative.update`` (all
+accumulated events one window forward, the new window back through every map, every older flow map carried forward, the
+pixel trajectories) and ``forward_prop_flow`` are one fused kernel each (``csrc/tef_validation.cu``); the images and
+metrics run through the CUDA primitives of ``taming_event_flow_b200.utils.iwe``; only the book-keeping around them
+(concatenating windows, averaging, variances) is left to torch.  It is pinned by golden vectors made from the unmodified
+reference (``tests/golden/make_golden.py``), not by the C oracle.  Batch size 1, like upstream (its index grids are
+batch-1, ``loss/flow_val.py:30-38``).
 """
+import ctypes
+
 import torch
 
+from .._lib import check, lib, ptr, require_cuda, stream
 from ..utils.iwe import event_propagation, get_event_flow, get_interpolation, interpolate, purge_unfeasible
+
+_l = ctypes.c_long
+_f = ctypes.c_float
 
 
 def _cat(old, new, dim=1):
@@ -58,6 +67,9 @@ class BaseValidation(torch.nn.Module):
     def update_base(self, flow_list, event_list, pol_mask, event_mask):
         """Append this window's events, finest flow map and event mask (upstream :75-114); the pass index is added to the
         caller's timestamps in place, as upstream does."""
+        require_cuda(flow_list[-1], event_list, pol_mask)
+        if event_list.shape[0] != 1 or flow_list[-1].shape[0] != 1:
+            raise RuntimeError("validation runs with batch size 1 (upstream builds batch-1 index grids, loss/flow_val.py:30-38)")
         event_list[:, :, 0:1] += self._passes
         self._event_ts = _cat(self._event_ts, self._window_ts(event_list))
         self._event_loc = _cat(self._event_loc, event_list[:, :, 1:3].clone())
@@ -76,17 +88,24 @@ class BaseValidation(torch.nn.Module):
             w = w * extra
         return torch.cat([interpolate(idx, w, self.res, polarity_mask=pm[:, :, c:c + 1]) for c in range(2)], dim=1)
 
+    def _prop_flow(self, maps_x, maps_y, first, n_maps, tref, out_x, out_y):
+        """Maps first..first+n_maps-1 of [1,P,H,W] carried to `tref` (None: each to the next time index), one splat and
+        one normalisation kernel for all of them; out_x/out_y [1,P,H,W] may be the inputs."""
+        H, W = self.res
+        acc = torch.empty((n_maps, 3, H, W), dtype=torch.float32, device=maps_x.device)
+        off = first * H * W * 4
+        check(lib().tef_val_forward_prop_flow(ctypes.c_void_p(maps_x.data_ptr() + off), ctypes.c_void_p(maps_y.data_ptr() + off), first, n_maps,
+                                              int(tref is None), _f(0.0 if tref is None else float(tref)), ptr(acc),
+                                              ctypes.c_void_p(out_x.data_ptr() + off), ctypes.c_void_p(out_y.data_ptr() + off), H, W, stream()),
+              "tef_val_forward_prop_flow")
+
     def forward_prop_flow(self, i, tref, flow_maps_x, flow_maps_y):
         """Flow map `i` carried forward to time `tref` by splatting it along itself (upstream :43-74)."""
-        px_flow = get_event_flow(flow_maps_x[:, i], flow_maps_y[:, i], self.indices)          # (y, x) per pixel
-        warped = event_propagation(i, self.indices, px_flow, tref)
-        warped, mask = purge_unfeasible(warped, self.indices_mask.clone(), self.res)
-        idx, w = get_interpolation(warped, self.res)
-        mask4, flow4 = _tile4(mask), _tile4(px_flow)
-        norm = interpolate(idx, w, self.res, polarity_mask=mask4)
-        fy = interpolate(idx, w * flow4[..., 0:1], self.res, polarity_mask=mask4) / (norm + 1e-9)
-        fx = interpolate(idx, w * flow4[..., 1:2], self.res, polarity_mask=mask4) / (norm + 1e-9)
-        return fx, fy
+        mx, my = flow_maps_x.contiguous().float(), flow_maps_y.contiguous().float()
+        require_cuda(mx, my)
+        fx, fy = torch.empty_like(mx), torch.empty_like(my)
+        self._prop_flow(mx, my, i, 1, tref, fx, fy)
+        return fx[:, i:i + 1], fy[:, i:i + 1]
 
     def window_events_base(self, round_idx=False):
         return self._pol_images(self._event_loc, self._event_pol_mask, round_idx)
@@ -166,8 +185,8 @@ class Linear(BaseValidation):
         if mask is None:
             mask = self.config["vis"]["mask_output"]
         fx, fy = self._flow_maps_x.clone(), self._flow_maps_y.clone()
-        for i in range(self._passes - 1):                                        # every older map carried to the newest time
-            fx[:, i:i + 1], fy[:, i:i + 1] = self.forward_prop_flow(i, self._passes - 1, self._flow_maps_x, self._flow_maps_y)
+        if self._passes > 1:                                                     # every older map carried to the newest time
+            self._prop_flow(self._flow_maps_x.contiguous(), self._flow_maps_y.contiguous(), 0, self._passes - 1, self._passes - 1, fx, fy)
         return self.window_flow_base(fx, fy, mask=mask)
 
     def window_iwe(self, mode=None, round_idx=False):
@@ -205,9 +224,9 @@ class Iterative(BaseValidation):
         self._clear_iterative()
 
     def update_fw_event_lists(self, event_list, event_pol_mask):
-        self._fw_event_warp_ts = _cat(self._fw_event_warp_ts, self._window_ts(event_list))
-        self._fw_event_loc = _cat(self._fw_event_loc, event_list[:, :, 1:3].clone())
-        self._fw_event_pol_mask = _cat(self._fw_event_pol_mask, event_pol_mask.clone())
+        self._fw_event_warp_ts = _cat(self._fw_event_warp_ts, self._window_ts(event_list)).contiguous()
+        self._fw_event_loc = _cat(self._fw_event_loc, event_list[:, :, 1:3].clone()).contiguous()
+        self._fw_event_pol_mask = _cat(self._fw_event_pol_mask, event_pol_mask.float().clone()).contiguous()
 
     def update_bw_event_lists(self, event_loc, event_pol_mask):
         self._bw_event_loc = _cat(self._bw_event_loc, event_loc.clone())
@@ -216,44 +235,39 @@ class Iterative(BaseValidation):
     def update(self, flow_list, event_list, pol_mask, event_mask):
         self.update_base(flow_list, event_list, pol_mask, event_mask)
         now = self._passes
-        last_x, last_y = self._flow_maps_x[:, -1], self._flow_maps_y[:, -1]
+        H, W = self.res
+        L, st = lib(), stream()
+        maps_x, maps_y = self._flow_maps_x.contiguous(), self._flow_maps_y.contiguous()          # [1,now+1,H,W]
+        last = now * H * W * 4
+        last_x, last_y = ctypes.c_void_p(maps_x.data_ptr() + last), ctypes.c_void_p(maps_y.data_ptr() + last)
 
         # all events so far, one window forward with the newest map (upstream :483-517)
         self.update_fw_event_lists(event_list, pol_mask)
-        flow = get_event_flow(last_x, last_y, self._fw_event_loc)
-        loc = event_propagation(self._fw_event_warp_ts, self._fw_event_loc, flow, now + 1)
-        self._fw_event_loc, self._fw_event_pol_mask = purge_unfeasible(loc, self._fw_event_pol_mask, self.res)
-        self._fw_event_warp_ts[...] = now + 1
+        check(L.tef_val_forward_step(last_x, last_y, ptr(self._fw_event_loc), ptr(self._fw_event_warp_ts), ptr(self._fw_event_pol_mask),
+                                     _f(now + 1), _l(self._fw_event_loc.shape[1]), H, W, st), "tef_val_forward_step")
 
         # the new window, back to time 0 through every map (upstream :519-556)
-        loc, mask = event_list[:, :, 1:3].clone(), pol_mask.clone()
-        ts = self._window_ts(event_list)
-        for k in range(now, -1, -1):
-            flow = get_event_flow(self._flow_maps_x[:, k], self._flow_maps_y[:, k], loc)
-            loc, mask = purge_unfeasible(event_propagation(ts, loc, flow, k), mask, self.res)
-            ts[...] = k
+        loc = event_list[:, :, 1:3].clone(memory_format=torch.contiguous_format)
+        mask = pol_mask.float().clone(memory_format=torch.contiguous_format)
+        ts = self._window_ts(event_list).contiguous()
+        check(L.tef_val_backward_chain(ptr(maps_x), ptr(maps_y), now + 1, ptr(loc), ptr(ts), ptr(mask), _l(loc.shape[1]), H, W, st),
+              "tef_val_backward_chain")
         self.update_bw_event_lists(loc, mask)
 
         # older flow maps carried one window forward (upstream :558-577)
         newest = flow_list[-1]
         self._fw_prop_flow_maps_x = _cat(self._fw_prop_flow_maps_x, newest[:, 0:1])
         self._fw_prop_flow_maps_y = _cat(self._fw_prop_flow_maps_y, newest[:, 1:2])
-        for i in range(now):
-            fx, fy = self.forward_prop_flow(i, i + 1, self._fw_prop_flow_maps_x, self._fw_prop_flow_maps_y)
-            self._fw_prop_flow_maps_x[:, i:i + 1] = fx
-            self._fw_prop_flow_maps_y[:, i:i + 1] = fy
+        if now > 0:
+            self._prop_flow(self._fw_prop_flow_maps_x, self._fw_prop_flow_maps_y, 0, now, None, self._fw_prop_flow_maps_x, self._fw_prop_flow_maps_y)
 
         # pixel trajectories (upstream :579-605)
-        H, W = self.res
-        idx = self.indices_map.clone() if self._flow_warping_indices is None else self._flow_warping_indices.clone()
-        valid = ((idx[:, 0:1] >= 0) & (idx[:, 0:1] <= H - 1.0) & (idx[:, 1:2] >= 0) & (idx[:, 1:2] <= W - 1.0)).float()
-        self._flow_out_mask += valid
-        cur = get_event_flow(last_x, last_y, idx.reshape(1, 2, -1).permute(0, 2, 1))
-        cur = cur.permute(0, 2, 1).reshape(1, 2, H, W)
-        moved = idx + cur * valid
-        self._accum_flow_map_x = moved[:, 1:2] - self.indices_map[:, 1:2]
-        self._accum_flow_map_y = moved[:, 0:1] - self.indices_map[:, 0:1]
-        self._flow_warping_indices = moved
+        if self._flow_warping_indices is None:
+            self._flow_warping_indices = self.indices_map.clone()
+        self._accum_flow_map_x = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
+        self._accum_flow_map_y = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
+        check(L.tef_val_trajectory_step(last_x, last_y, ptr(self._flow_warping_indices), ptr(self._flow_out_mask), ptr(self._accum_flow_map_x),
+                                        ptr(self._accum_flow_map_y), H, W, st), "tef_val_trajectory_step")
         self._passes += 1
 
     def window_events(self, round_idx=False):

@@ -53,3 +53,41 @@ def test_flow_val_golden(name):
     assert checked >= 27
     m.reset()
     assert m.num_passes == 0
+
+
+def test_forward_prop_flow_matches_operator_route():
+    """The fused splat/normalise kernels against the same computation spelled out with the stand-alone operators
+    (upstream loss/flow_val.py:43-74 line by line)."""
+    from taming_event_flow_b200.loss import flow_val as fv
+    from taming_event_flow_b200.utils.iwe import event_propagation, get_event_flow, get_interpolation, interpolate, purge_unfeasible
+
+    H, W, P = 37, 53, 4
+    g = torch.Generator().manual_seed(2)
+    mx = (torch.randn(1, P, H, W, generator=g) * 4).cuda()
+    my = (torch.randn(1, P, H, W, generator=g) * 4).cuda()
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
+    m = fv.Iterative(cfg, "cuda")
+    for i, tref in ((0, 1), (2, 3), (1, 3)):
+        px_flow = get_event_flow(mx[:, i], my[:, i], m.indices)
+        warped, mask = purge_unfeasible(event_propagation(i, m.indices, px_flow, tref), m.indices_mask.clone(), m.res)
+        idx, w = get_interpolation(warped, m.res)
+        mask4, flow4 = torch.cat([mask] * 4, 1), torch.cat([px_flow] * 4, 1)
+        norm = interpolate(idx, w, m.res, polarity_mask=mask4)
+        want_y = interpolate(idx, w * flow4[..., 0:1], m.res, polarity_mask=mask4) / (norm + 1e-9)
+        want_x = interpolate(idx, w * flow4[..., 1:2], m.res, polarity_mask=mask4) / (norm + 1e-9)
+        fx, fy = m.forward_prop_flow(i, tref, mx, my)
+        assert fx.shape == (1, 1, H, W) and fy.shape == (1, 1, H, W)
+        for got, want in ((fx, want_x), (fy, want_y)):
+            linf, l2 = rel_err(got.cpu().numpy(), want.cpu().numpy())
+            assert linf < 1e-6 and l2 < 1e-6, (i, tref, linf, l2)
+        assert torch.equal(norm == 0, fx == 0)                                # untouched pixels stay exactly 0
+
+
+def test_validation_rejects_batches():
+    from taming_event_flow_b200.loss import flow_val as fv
+
+    cfg = {"loader": {"resolution": [8, 8]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
+    m = fv.Iterative(cfg, "cuda")
+    with pytest.raises(RuntimeError):
+        m.update([torch.zeros(2, 2, 8, 8, device="cuda")], torch.zeros(2, 5, 4, device="cuda"), torch.zeros(2, 5, 2, device="cuda"),
+                 torch.zeros(2, 1, 8, 8, device="cuda"))
