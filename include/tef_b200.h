@@ -185,6 +185,24 @@ int tef_split_events(const float *event_list, const float *pol_mask, const long 
                      float *g_events, float *g_mask, long Ng, float *d_events, float *d_mask, long Nd, void *stream);
 
 /* ------------------------------------------------------------------------- */
+/* loss/flow.py:131-209 -- the smoothness priors on the packed   */
+/* flow maps written by tef_pack_flow / tef_update_pass: [F][P][B] maps, of which  */
+/* the first n passes have been given to update()                                 */
+/* ------------------------------------------------------------------------- */
+/* floats of scratch either prior needs */
+long tef_flow_smoothing_scratch(int B, int H, int W, int n, int F);
+/* flow_spatial_smoothing (:170-209): out [B] = per-sample value before the weight (the caller sums and scales) */
+int tef_flow_spatial_smoothing(const float *packed_flow, int B, int H, int W, int P, int F, int n, float *scratch, float *out, void *stream);
+/* its gradient: gout [B] (device) -> packed_grad, the dual-phase layout tef_unpack_flow_grad reads (zeroed inside) */
+int tef_flow_spatial_smoothing_bwd(const float *packed_flow, const float *gout, float *packed_grad, int B, int H, int W, int P, int F, int n,
+                                   void *stream);
+/* flow_temporal_smoothing (:131-168): out [B]; sums [F][n-1][B][2] (masked sum, valid pixels) is kept for the backward */
+int tef_flow_temporal_smoothing(const float *packed_flow, int B, int H, int W, int P, int F, int n, float *scratch, float *sums, float *out,
+                                void *stream);
+int tef_flow_temporal_smoothing_bwd(const float *packed_flow, const float *sums, const float *gout, float *packed_grad, int B, int H, int W,
+                                    int P, int F, int n, void *stream);
+
+/* ------------------------------------------------------------------------- */
 /* loss/flow_val.py -- fused stages of the validation update; */
 /* batch size 1 like upstream; maps are planar [H][W] (x and y flow separately) */
 /* ------------------------------------------------------------------------- */

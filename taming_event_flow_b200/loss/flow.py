@@ -90,6 +90,49 @@ class _CMLoss(torch.autograd.Function):
         return (None, None) + tuple(out)
 
 
+class _Smoothness(torch.autograd.Function):
+    """Per-sample value [B] of one smoothness prior over the first `n` passes of the window; backward = its gradient
+    w.r.t. every flow map of those passes."""
+
+    @staticmethod
+    def forward(ctx, module, w, temporal, n, *flat_flows):
+        F, B, H, W = w.shape
+        P = module._max_passes()
+        dev = w.packed.device
+        L = lib()
+        L.tef_flow_smoothing_scratch.restype = ctypes.c_long
+        scratch = torch.empty((max(L.tef_flow_smoothing_scratch(B, H, W, n, F), 1),), dtype=torch.float32, device=dev)
+        out = torch.empty((B,), dtype=torch.float32, device=dev)
+        sums = None
+        if temporal:
+            sums = torch.empty((F, n - 1, B, 2), dtype=torch.float32, device=dev)
+            check(L.tef_flow_temporal_smoothing(ptr(w.packed), B, H, W, P, F, n, ptr(scratch), ptr(sums), ptr(out), stream()), "tef_flow_temporal_smoothing")
+        else:
+            check(L.tef_flow_spatial_smoothing(ptr(w.packed), B, H, W, P, F, n, ptr(scratch), ptr(out), stream()), "tef_flow_spatial_smoothing")
+        ctx.module, ctx.w, ctx.temporal, ctx.n, ctx.sums = module, w, temporal, n, sums
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w, n = ctx.w, ctx.n
+        F, B, H, W = w.shape
+        P = ctx.module._max_passes()
+        dev = w.packed.device
+        Wp = (W + 3) & ~1
+        gpacked = torch.empty((F * P * B * 2 * H * Wp * 2,), dtype=torch.float32, device=dev)
+        grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)
+        g = gout.detach().float().contiguous()
+        L = lib()
+        if ctx.temporal:
+            check(L.tef_flow_temporal_smoothing_bwd(ptr(w.packed), ptr(ctx.sums), ptr(g), ptr(gpacked), B, H, W, P, F, n, stream()),
+                  "tef_flow_temporal_smoothing_bwd")
+        else:
+            check(L.tef_flow_spatial_smoothing_bwd(ptr(w.packed), ptr(g), ptr(gpacked), B, H, W, P, F, n, stream()), "tef_flow_spatial_smoothing_bwd")
+        check(L.tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, 0, stream()), "tef_unpack_flow_grad")
+        out = [grads[t, f] if t < n else None for t in range(len(w.flows)) for f in range(F)]
+        return (None, None, None, None) + tuple(out)
+
+
 class BaseEventWarping(torch.nn.Module):
     """Base class of the CM losses (upstream ``loss/flow.py:14-213``)."""
 
@@ -342,50 +385,22 @@ class BaseEventWarping(torch.nn.Module):
             loss = loss / (nonzero.sum(1) + 1e-9)
         return loss.sum()
 
-    # Smoothness priors (upstream loss/flow.py:131-209).  Off in every shipped config (`Null` weights) and not on the
-    # accelerated path: they are evaluated on the flow tensors the caller handed to `update` with ordinary autograd
-    # (the one gather they need goes through the `get_event_flow` kernel).
-    def _flow_stack(self, f):
-        """[B, passes, 2, H, W] (ch0 = x, ch1 = y) of flow scale `f` over all passes given to `update`."""
-        return torch.stack([per_pass[f] for per_pass in self._win.flows], dim=1)
+    # Smoothness priors (upstream loss/flow.py:131-209; `Null` in every shipped config): fused kernels on the packed flow
+    # maps `update` built (csrc/tef_cm_smooth.cu), gradients to the same flow tensors the CM loss differentiates.
+    def _smoothness(self, temporal):
+        w = self._win
+        if w.packed is None:
+            raise IndexError("no flow maps: call update() first")
+        flat = [fl for per_pass in w.flows for fl in per_pass]
+        return _Smoothness.apply(self, w, temporal, self._passes, *flat).sum()
 
     def flow_spatial_smoothing(self):
         """Charbonnier penalty on horizontal, vertical and both diagonal flow differences (upstream :170-209)."""
-        eps = 1e-6
-        total = 0
-        for f in range(self._num_flows):
-            fl = self._flow_stack(f)                                            # [B,P,2,H,W]
-            pairs = ((fl[..., :, :-1], fl[..., :, 1:]), (fl[..., :-1, :], fl[..., 1:, :]),
-                     (fl[..., :-1, :-1], fl[..., 1:, 1:]), (fl[..., 1:, :-1], fl[..., :-1, 1:]))
-            acc = 0
-            for a, b in pairs:
-                d = torch.sqrt((a - b) ** 2 + eps).sum(2)                       # x and y components
-                acc = acc + d.flatten(2).mean(2).mean(1)
-            total = total + acc / 4
-        total = total / self._num_flows
-        return self.flow_spat_smooth_weight * total.sum()
+        return self.flow_spat_smooth_weight * self._smoothness(False)
 
     def flow_temporal_smoothing(self):
         """Charbonnier penalty between each flow map and the next one sampled where the flow points (upstream :131-168)."""
-        from ..utils.iwe import get_event_flow
-
-        H, W = self.res
-        dev = self._win.flows[0][0].device
-        yy, xx = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32), torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
-        grid = torch.stack([yy, xx], 0).unsqueeze(0)                           # [1,2,H,W] (y, x)
-        total = 0
-        for f in range(self._num_flows):
-            fl = self._flow_stack(f)
-            B = fl.shape[0]
-            for j in range(fl.shape[1] - 1):
-                cur = torch.stack([fl[:, j, 1], fl[:, j, 0]], 1)                # (y, x) order
-                tgt = (grid + cur).reshape(B, 2, -1).permute(0, 2, 1)           # [B,HW,2]
-                inside = ((tgt[..., 0] >= 0) & (tgt[..., 0] <= H - 1.0) & (tgt[..., 1] >= 0) & (tgt[..., 1] <= W - 1.0)).float()
-                nxt = get_event_flow(fl[:, j + 1, 0], fl[:, j + 1, 1], tgt)     # [B,HW,2] (y, x)
-                diff = torch.sqrt((cur.reshape(B, 2, -1).permute(0, 2, 1) - nxt) ** 2 + 1e-9).sum(2)
-                total = total + (diff * inside).sum(1) / (inside.sum(1) + 1e-9)
-        total = total / self._num_flows / (self._passes - 1)
-        return self.flow_temp_smooth_weight * total.sum()
+        return self.flow_temp_smooth_weight * self._smoothness(True)
 
     def forward(self):
         raise NotImplementedError

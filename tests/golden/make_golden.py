@@ -253,6 +253,44 @@ def make_flow_val_cases():
     print("flow_val cases written")
 
 
+def make_smoothness_cases():
+    """loss/flow.py:131-209: each smoothness prior on its own (weight 1), value and gradients from the
+    unmodified reference's autograd, fp32 and fp64, plus the value after fewer updates than passes_loss."""
+    out = {}
+    B, P, H, W, F = 2, 4, 28, 36, 2
+    seq = syn.make_sequence(21, B, P, 50, 0, H, W, F_scales=F, sigma=4.0)
+    cfg = syn.loss_config(H, W, B, P, 1, "two")
+    cfg["loss"]["flow_spat_smooth_weight"], cfg["loss"]["flow_temp_smooth_weight"] = 1.0, 1.0
+    out.update({"B": B, "P": P, "H": H, "W": W, "F": F})
+    for t in range(P):
+        out["ev%d" % t], out["mk%d" % t] = seq["events"][t].numpy(), seq["masks"][t].numpy()
+        for f in range(F):
+            out["flow%d_%d" % (t, f)] = seq["flows"][t][f].numpy()
+    for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+        torch.set_default_dtype(dtype)
+        try:
+            m = Iterative(copy.deepcopy(cfg), "cpu")
+            flows = [[f.to(dtype).clone().requires_grad_(True) for f in fl] for fl in seq["flows"]]
+            empty_e, empty_m = torch.zeros(B, 0, 4, dtype=dtype), torch.zeros(B, 0, 2, dtype=dtype)
+            for t in range(P):
+                m.update(flows[t], seq["events"][t].to(dtype).clone(), seq["masks"][t].to(dtype).clone(), empty_e, empty_m)
+                if t == 1:
+                    out["spat_2passes_" + tag] = m.flow_spatial_smoothing().item()
+                    out["temp_2passes_" + tag] = m.flow_temporal_smoothing().item()
+            for name, fn in (("spat", m.flow_spatial_smoothing), ("temp", m.flow_temporal_smoothing)):
+                for fl in flows:
+                    for f in fl:
+                        f.grad = None
+                val = fn()
+                val.backward()
+                out["%s_%s" % (name, tag)] = val.item()
+                out["%s_grad_%s" % (name, tag)] = np.stack([np.stack([flows[t][f].grad.numpy() for t in range(P)]) for f in range(F)])
+        finally:
+            torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(HERE, "smoothness.npz"), **out)
+    print("smoothness cases written", out["spat_32"], out["temp_32"])
+
+
 def make_loader_cases():
     """dataloader/base.py: the static methods of the UNMODIFIED BaseDataLoader on three ragged windows."""
     import types
@@ -298,4 +336,5 @@ if __name__ == "__main__":
     make_encoding_cases()
     make_flow_val_cases()
     make_loader_cases()
+    make_smoothness_cases()
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
