@@ -262,7 +262,8 @@ def measure_l2_rates(L, dev):
     buf = torch.zeros(64 << 20, dtype=torch.uint8, device=dev)     # L2-resident (126 MB L2)
     out = {}
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for name, kind, mode in (("red_v4_spread", 0, 0), ("red_v4_local", 0, 1), ("gather8_spread", 1, 0), ("gather8_local", 1, 1)):
+    for name, kind, mode in (("red_v4_spread", 0, 0), ("red_v4_local", 0, 1), ("gather8_spread", 1, 0), ("gather8_local", 1, 1),
+                             ("gather16_spread", 2, 0), ("gather16_local", 2, 1)):
         ops = ctypes.c_long()
         best = 1e30
         for rep in range(3):
@@ -278,16 +279,17 @@ def measure_l2_rates(L, dev):
 
 
 def cm_lane_ops(wl, kernel):
-    """Algorithmic lane-op counts of the two Iterative kernels (mode two, S = 1): per event and flow scale P+1 chain steps of
-    4 gathers, ~0.8 P reference times of 2 red.v4 (forward); ~0.8 P nodes of 4 + 4 gathers and 2 red.v4 (backward)."""
+    """Lane-op counts of the two Iterative kernels as issued (mode two, S = 1), per event and flow scale: P+1 chain steps of
+    two 16-byte tap-row gathers and ~0.8 P reference times of 2 red.v4 (forward); ~0.8 P nodes of 2 + 2 16-byte gathers
+    (gradient-image corner pairs, tap rows) and 2 red.v4 (backward)."""
     E = events_per_step(wl) * wl["F"]
     Eg = wl["B"] * wl["P"] * wl["N"] * wl["F"]
     P = wl["P"]
     pairs = sum(min(P, tr + P // 2) - max(0, tr - P // 2) for tr in range(P + 1)) / P     # (event, tref) pairs per event: 8 at P = 10
     if kernel == "iter_fwd_kernel":
-        return {"gathers": 4 * (P + 1) * E, "reds": 2 * pairs * E}
+        return {"gathers": 2 * (P + 1) * E, "reds": 2 * pairs * E}
     if kernel == "iter_bwd_kernel":
-        return {"gathers": 8 * pairs * Eg, "reds": 2 * pairs * Eg}
+        return {"gathers": 4 * pairs * Eg, "reds": 2 * pairs * Eg}
     return None
 
 
@@ -514,10 +516,10 @@ def run_ours(args, wl):
         for k in ("iter_fwd_kernel", "iter_bwd_kernel"):
             ops = cm_lane_ops(wl, k) if k in kern else None
             if ops:
-                t_g = ops["gathers"] / (rates["gather8_local"] * 1e9)
+                t_g = ops["gathers"] / (rates["gather16_local"] * 1e9)
                 t_r = ops["reds"] / (rates["red_v4_local"] * 1e9)
                 t_min = max(t_g, t_r)                   # roofline: the slower of the two resources, each at its measured peak
-                l2["kernels"][k] = {"gathers": int(ops["gathers"]), "red_v4": int(ops["reds"]), "ms_gathers_at_peak": round(t_g * 1e3, 4),
+                l2["kernels"][k] = {"gathers16": int(ops["gathers"]), "red_v4": int(ops["reds"]), "ms_gathers_at_peak": round(t_g * 1e3, 4),
                                     "ms_reds_at_peak": round(t_r * 1e3, 4), "bound": "gather" if t_g >= t_r else "red",
                                     "frac": round(t_min * 1e3 / kern[k]["ms_avg"], 4)}
         cpu = run_cpu_baseline(wl)

@@ -224,7 +224,7 @@ int tef_val_forward_prop_flow(const float *mapsx, const float *mapsy, int first,
 int tef_val_trajectory_step(const float *mapx, const float *mapy, float *idx, float *out_mask, float *accx, float *accy, int H, int W,
                             void *stream);
 
-/* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers;
+/* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers, 2 = 16-byte gathers;
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */
 int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream);
 

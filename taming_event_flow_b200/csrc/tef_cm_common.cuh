@@ -342,6 +342,7 @@ __device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const
         if (!(tp.ok[2 * ky] || tp.ok[2 * ky + 1])) continue;
         const float cl = tp.ok[2 * ky] ? dt * tp.w[2 * ky] : 0.0f;
         const float cr = tp.ok[2 * ky + 1] ? dt * tp.w[2 * ky + 1] : 0.0f;
+        if (cl == 0.0f && cr == 0.0f) continue;                     // e.g. the bottom row of a sample at an integer position (an event's own pixel)
         const long off = (long)phase * g.plane + (long)(tp.y0 + ky) * g.Wp + col;
         if (!DET) {
             red_add_v4(gmap_phase0 + off, cl * gpx, cl * gpy, cr * gpx, cr * gpy);

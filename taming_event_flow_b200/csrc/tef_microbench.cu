@@ -38,11 +38,30 @@ __global__ void __launch_bounds__(kThreads) mb_gather_kernel(const float2 *__res
     if (acc == 123.456f) *sink = acc;
 }
 
+// 16-byte gathers: what the event kernels issue since the dual-phase layouts (one tap row / corner pair per load)
+__global__ void __launch_bounds__(kThreads) mb_gather16_kernel(const float4 *__restrict__ buf, uint32_t slots, int iters, int mode, float *sink) {
+    uint32_t s = (blockIdx.x * kThreads + threadIdx.x) * 2654435761u + 777u;
+    const uint32_t warp_base = ((blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 40503u * 256u) & (slots - 1);
+    float acc = 0.f;
+    for (int i = 0; i < iters; i += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t r = lcg(s) >> 8;
+            const uint32_t a = mode == 0 ? (r & (slots - 1)) : ((warp_base + (r & 255u) + (uint32_t)(i + k) * 64u) & (slots - 1));
+            v[k] = __ldg(buf + a);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
 }  // namespace tef
 
 using namespace tef;
 
-// kind 0: red.v4, kind 1: 8-byte gather.  buf: at least `bytes` (power of two) of device memory.  Launches
+// kind 0: red.v4, kind 1: 8-byte gather, kind 2: 16-byte gather.  buf: at least `bytes` (power of two) of device memory.  Launches
 // 148*8 CTAs x 256 threads x iters operations; returns 0 and the operation count through *ops.
 extern "C" int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream) {
     if (!buf || bytes < (1 << 20) || (bytes & (bytes - 1)) || iters < 4) return TEF_EINVAL;
@@ -50,7 +69,9 @@ extern "C" int tef_microbench(int kind, int mode, void *buf, long bytes, int ite
     const int ctas = 148 * 8;
     ProfScope ps(K_MICROBENCH, st);
     if (kind == 0) mb_red_kernel<<<ctas, kThreads, 0, st>>>((float4 *)buf, (uint32_t)(bytes / 16), iters, mode);
-    else mb_gather_kernel<<<ctas, kThreads, 0, st>>>((const float2 *)buf, (uint32_t)(bytes / 8), iters & ~3, mode, (float *)buf);
+    else if (kind == 1) mb_gather_kernel<<<ctas, kThreads, 0, st>>>((const float2 *)buf, (uint32_t)(bytes / 8), iters & ~3, mode, (float *)buf);
+    else if (kind == 2) mb_gather16_kernel<<<ctas, kThreads, 0, st>>>((const float4 *)buf, (uint32_t)(bytes / 16), iters & ~3, mode, (float *)buf);
+    else return TEF_EINVAL;
     if (ops) *ops = (long)ctas * kThreads * (kind == 0 ? iters : (iters & ~3));
     return (int)cudaGetLastError();
 }

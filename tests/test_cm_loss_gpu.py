@@ -78,6 +78,9 @@ CASES = [
     ("iterative", 2, 8, 2000, 0, 64, 80, 1, 2, "one", 2.0, False, False, "uniform"),
     ("iterative", 1, 10, 20000, 0, 480, 640, 1, 1, "two", 3.0, False, True, "uniform"),
     ("iterative", 1, 24, 1500, 500, 64, 64, 1, 1, "two", 1.0, False, True, "uniform"),
+    ("iterative", 1, 31, 300, 100, 40, 48, 8, 5, "one", 1.0, False, True, "uniform"),       # TEF_MAX_PASSES, TEF_MAX_FLOWS, 5 scales
+    ("iterative", 1, 16, 800, 200, 48, 64, 1, 2, "four", 2.0, False, False, "uniform"),
+    ("linear", 1, 31, 300, 100, 40, 48, 8, 5, "two", 1.0, True, True, "uniform"),
     ("linear", 8, 10, 2000, 2000, 128, 128, 2, 1, "two", 3.0, False, True, "uniform"),
     ("linear", 2, 8, 3000, 1000, 96, 112, 1, 3, "two", 3.0, True, False, "edges"),
 ]
@@ -87,7 +90,8 @@ CASES = [
 def test_oracle_parity_seeded(case):
     kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, dist = case
     seq = syn.make_sequence(11, B, P, N, Nd, H, W, F, sigma, ragged, dist)
-    cfg = syn.loss_config(H, W, B, P, S, mode)
+    P_cfg = P // 2 if (mode == "four" and kind == "iterative") else P      # Iterative.__init__ doubles it (loss/flow.py:422-423)
+    cfg = syn.loss_config(H, W, B, P_cfg, S, mode)
     g = _run_gpu(kind, cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], border=border)
     oc = orc.make_cfg(B, H, W, P, F, S, mode, border)
     fn = orc.iterative if kind == "iterative" else orc.linear
