@@ -130,6 +130,17 @@ def cpu_port_step(seq, wl):
     return time.perf_counter() - t0, out
 
 
+def cpu_threads():
+    """All host threads this process may use, set explicitly (torchrun exports OMP_NUM_THREADS=1); returns the team size in effect."""
+    from oracle import cm_oracle as orc
+
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count()
+    return orc.set_threads(want)
+
+
 def cpu_sample_size(wl):
     # bounded sample: same resolution / passes / batch, fewer events per window
     return min(wl["N"], 200_000)
@@ -138,13 +149,14 @@ def cpu_sample_size(wl):
 def run_cpu_baseline(wl, repeats=2):
     n = cpu_sample_size(wl)
     seq = fast_sequence(1234, wl, n_override=n)
+    threads = cpu_threads()
     cpu_port_step(seq, wl)  # warm-up (page faults, OpenMP pool)
     best = min(cpu_port_step(seq, wl)[0] for _ in range(repeats))
     ev = events_per_step(wl, n)
     return {
-        "value": ev / best / 1e6, "unit": "Mevents/s", "cores": os.cpu_count(), "kind": "port",
+        "value": ev / best / 1e6, "unit": "Mevents/s", "cores": threads, "kind": "port",
         "sample": "%s with %d events/window (%d events/step), oracle/cm_oracle.c fwd+bwd, OpenMP on %d threads, best of %d"
-                  % (wl["name"], n, ev, os.cpu_count(), repeats),
+                  % (wl["name"], n, ev, threads, repeats),
     }
 
 
@@ -157,6 +169,7 @@ def run_reference_arm(args, wl):
     from oracle import cm_oracle as orc
 
     orc.lib()                      # compile / load the port before anything is timed
+    threads = cpu_threads()
     for _ in range(args.warmup):
         cpu_port_step(seq, wl)
     t0 = time.perf_counter()
@@ -166,12 +179,12 @@ def run_reference_arm(args, wl):
     ev = events_per_step(wl, n)
     v = ev * args.steps / dt / 1e6
     sample = "%s with %d events/window (%d events/step), CPU port of the reference algorithm (oracle/cm_oracle.c), OpenMP on %d threads" % (
-        wl["name"], n, ev, os.cpu_count())
+        wl["name"], n, ev, threads)
     line = {
         "impl": "reference", "metric": "cm_loss_fwd_bwd_throughput", "value": v, "unit": "Mevents/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(wl),
-        "cpu_baseline": {"value": v, "unit": "Mevents/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mevents/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

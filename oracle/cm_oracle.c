@@ -42,3 +42,12 @@ int orc_num_slots(const orc_cfg *c, int linear)
     return linear ? linear_slots_f32(c, NULL) : build_slots_f32(c, NULL);
 }
 int orc_version(void) { return 1; }
+
+/* OpenMP team size of the timed CPU baseline: launchers such as torchrun export OMP_NUM_THREADS=1, so bench.py sets it
+   explicitly and reports what it got */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int orc_set_threads(int n) { (void)n; return 1; }
+#endif

@@ -16,5 +16,6 @@ typedef struct {
 
 int orc_num_slots(const orc_cfg *c, int linear);
 int orc_version(void);
+int orc_set_threads(int n);   /* returns the OpenMP team size in effect */
 
 #endif

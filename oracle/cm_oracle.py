@@ -49,6 +49,11 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """Set (n > 0) and return the OpenMP team size the oracle runs with."""
+    return int(lib().orc_set_threads(int(n)))
+
+
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 

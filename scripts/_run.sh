@@ -1,1 +1,3 @@
-python -m pytest tests/test_cm_loss_gpu.py -x -q 2>&1 | tail -40
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu_h.json 2> gpurun_out/bench_2gpu_h.err
+echo "exit $?"; tail -c 400 gpurun_out/bench_2gpu_h.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-600

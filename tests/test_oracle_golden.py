@@ -105,3 +105,10 @@ def test_error_codes_mirror_reference_failures():
     cfg = orc.make_cfg(c["B"], c["H"], c["W"], 4, c["F"], 1, "four", True)
     with pytest.raises(orc.OracleError):
         orc.iterative(cfg, c["flow_list"], c["events"], c["masks"], c["d_events"], c["d_masks"])
+
+
+def test_oracle_thread_control():
+    """bench.py sets the OpenMP team size explicitly (torchrun exports OMP_NUM_THREADS=1) and reports what it got."""
+    before = orc.set_threads(0)
+    assert orc.set_threads(2) == 2
+    assert orc.set_threads(before) == before
