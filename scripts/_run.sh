@@ -1,3 +1,4 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu_h.json 2> gpurun_out/bench_2gpu_h.err
-echo "exit $?"; tail -c 400 gpurun_out/bench_2gpu_h.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-600
+python -m pytest tests/test_cm_loss_gpu.py tests/test_properties_fullsize_gpu.py -x -q 2>&1 | tail -3
+for wl in iterative_480x640_1Mev iterative_128x128_b8_f4 iterative_480x640_1Mev_edges; do
+  python scripts/kernel_times.py --workload $wl 2>&1 | tail -1 | cut -c1-330
+done

@@ -255,9 +255,11 @@ __device__ __forceinline__ float2 *img_plane(float2 *slot_base, const ImgGeom &g
 static __device__ __noinline__ void splat_second_polarity(float2 *plane1, float wl, float tl, float wr, float tr, float my) {
     red_add_v4(plane1, wl * my, tl * my, wr * my, tr * my);
 }
-static __device__ __noinline__ void grad_second_polarity(const float2 *plane1, float nts, float my, float &gl, float &gr) {
+// (returns by value: reference parameters of an out-of-line function live on the stack, and the caller then stores and
+// reloads them around every -- almost never taken -- call: profiles/r1_h showed 23 M local-memory wavefronts from that)
+static __device__ __noinline__ float2 grad_second_polarity(const float2 *plane1, float nts, float my) {
     const float4 u = __ldg(reinterpret_cast<const float4 *>(plane1));
-    gl = gl + my * (u.x + nts * u.y); gr = gr + my * (u.z + nts * u.w);
+    return make_float2(my * (u.x + nts * u.y), my * (u.z + nts * u.w));
 }
 
 template <bool INSIDE, bool DET>
@@ -324,7 +326,10 @@ __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, c
         const int off = (int)c.cy[ky] * g.Wp + col;
         const float4 v = __ldg(reinterpret_cast<const float4 *>(g0 + off));
         float gl = m0 * (v.x + nts * v.y), gr = m0 * (v.z + nts * v.w);
-        if (!binary) grad_second_polarity(slot_base + (long)(phase * 2 + 1) * g.plane + off, nts, m.y, gl, gr);
+        if (!binary) {
+            const float2 add = grad_second_polarity(slot_base + (long)(phase * 2 + 1) * g.plane + off, nts, m.y);
+            gl = gl + add.x; gr = gr + add.y;
+        }
         if (c.okx[0]) { gy += gl * dy[ky] * c.wx[0]; gx += gl * c.wy[ky] * dx[0]; }
         if (c.okx[1]) { gy += gr * dy[ky] * c.wx[1]; gx += gr * c.wy[ky] * dx[1]; }
     }
