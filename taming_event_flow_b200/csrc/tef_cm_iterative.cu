@@ -193,8 +193,16 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     const long gslot = 4 * p.ig.plane;
     const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
 
+    // scale 0 (the only one in every shipped config) is kept in registers: the window table is otherwise re-read from
+    // shared memory at every node (14 M broadcast loads per launch, 11 % of the kernel's L1TEX wavefronts)
+    const int w0_tr0 = (has & 1u) ? sw[0].tr0 : 1, w0_tr1 = (has & 1u) ? sw[0].tr1 : 0, w0_slot0 = sw[0].slot0;
+    const float w0_fdelta = sw[0].fdelta, w0_rdelta = sw[0].rdelta;
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
-        for (int s = 0; s < p.sc.S; ++s) {
+        if (tr >= w0_tr0 && tr <= w0_tr1) {
+            const float nts = 1.0f - div_const(fabsf((float)tr - ts), w0_fdelta, w0_rdelta);
+            iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+        }
+        for (int s = 1; s < p.sc.S; ++s) {
             if (!((has >> s) & 1u) || tr < sw[s].tr0 || tr > sw[s].tr1) continue;
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), sw[s].fdelta, sw[s].rdelta);
             iwe_grad<true>(img_fb + (long)(sw[s].slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
