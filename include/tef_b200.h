@@ -71,6 +71,9 @@ typedef struct tef_cm_desc {
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
     void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
     void *gimg;            /* deterministic mode only: gradient images float2 [F][B][slots][phase][pol][H][Wp] */
+    int hist_done;         /* 1: every tef_update_pass of this window already counted its events into sort_bins (fused histogram),
+                              the forward call then skips its own histogram pass */
+    int reserved_;
 } tef_cm_desc;
 
 /* buffer sizes for the events currently described by `d`; out[11] =
@@ -93,8 +96,9 @@ int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B,
 /* backward counterpart: packed gradient -> [P][F][B][2][H][W] */
 int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream);
 
-/* The whole of Iterative.update / Linear.update in one call (two launches): tef_pack_flow for the F maps of pass `t`
-   plus tef_stage_events for the gradient-carrying set [0] and the detached set [1]. */
+/* The whole of Iterative.update / Linear.update in one call and one launch: tef_pack_flow for the F maps of pass `t`
+   plus tef_stage_events for the gradient-carrying set [0] and the detached set [1]; optionally the staging kernel also
+   builds the histogram of the tile sort, which saves the forward call a pass over the events. */
 typedef struct tef_update_desc {
     int F, t, P, B, H, W;
     const void *flow_maps[TEF_MAX_FLOWS];  /* [B][2][H][W] each                                   */
@@ -106,6 +110,11 @@ typedef struct tef_update_desc {
     long rows[2];                          /* B * n                                               */
     float pass_index[2];
     const float *ts_override[2];           /* round_ts device scalars or NULL                     */
+    void *sort_bins;                       /* optional fused tile-sort histogram: int [2*P*B*tiles*128 + 1] of the window, where
+                                              tiles = ceil(W/16)*ceil(H/8); segment (set k, pass t) owns bins from
+                                              (k*P + t)*B*tiles*128 (the layout tef_*_forward expects with hist_done = 1) */
+    int hist;                              /* 1: count this pass' events into sort_bins            */
+    int zero_bins;                         /* 1: clear sort_bins first (first update of a window)  */
 } tef_update_desc;
 int tef_update_pass(const tef_update_desc *u, void *stream);
 

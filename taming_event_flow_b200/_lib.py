@@ -51,6 +51,8 @@ class CmDesc(ctypes.Structure):
             ("posbuf", ctypes.c_void_p),
             ("alivebuf", ctypes.c_void_p),
             ("gimg", ctypes.c_void_p),
+            ("hist_done", ctypes.c_int),
+            ("reserved_", ctypes.c_int),
         ]
     )
 
@@ -69,6 +71,9 @@ class UpdateDesc(ctypes.Structure):
             ("rows", ctypes.c_long * 2),
             ("pass_index", ctypes.c_float * 2),
             ("ts_override", ctypes.c_void_p * 2),
+            ("sort_bins", ctypes.c_void_p),
+            ("hist", ctypes.c_int),
+            ("zero_bins", ctypes.c_int),
         ]
     )
 

@@ -32,6 +32,14 @@ struct SortGeom {
     float4 *rec;                     // sorted rows, 32 B each: (ts, y, x, sample index bits | mask+, mask-, 0, 0)
 };
 
+// Sort key of one event inside its segment: (sample, 16x8-pixel tile, pixel).  `first_bin` is the segment's first bin.
+__device__ __forceinline__ int sort_bin(int first_bin, int tiles_x, int tiles, int H, int W, int b, float y, float x) {
+    const int iy = (int)fminf(fmaxf(floorf(y), 0.0f), (float)(H - 1));
+    const int ix = (int)fminf(fmaxf(floorf(x), 0.0f), (float)(W - 1));
+    const int tile = (iy >> 3) * tiles_x + (ix >> 4);
+    return first_bin + (b * tiles + tile) * 128 + ((iy & 7) << 4) + (ix & 15);
+}
+
 // One entry per temporal scale (loss/flow.py:42-44, :434-441, :657-668)
 struct ScaleTable {
     int S;
@@ -63,7 +71,7 @@ __device__ __forceinline__ void red_add_i64(long long *addr, long long v) {
 }
 
 struct CmParams {
-    int B, H, W, P, F, mode, border, loss_scaling, nslots, linear, det, nchunks;
+    int B, H, W, P, F, mode, border, loss_scaling, nslots, linear, det, nchunks, hist_done;
     Res res;
     ImgGeom ig;
     const float2 *flow;
@@ -170,10 +178,20 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     SortGeom &g = p.sort;
     g.B = d->B; g.H = d->H; g.W = d->W;
     g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
-    for (int s = 0; s <= ns; ++s) p.seg.first_bin[s] = s * d->B * g.tiles * 128;
+    // bins are laid out by FIXED segment slots (set * P + pass), empty passes included, so that tef_update_pass can count
+    // a pass before the later ones are known; the detached set's slots exist only if it has any rows
+    const int per_seg = d->B * g.tiles * 128;
+    bool any_detached = false;
+    for (int s = 0; s < ns; ++s) {
+        p.seg.first_bin[s] = (p.seg.set[s] * d->P + p.seg.pass[s]) * per_seg;
+        any_detached |= p.seg.set[s] == 1;
+    }
+    const int nslots_sort = d->P * (any_detached ? 2 : 1);
+    p.seg.first_bin[ns] = nslots_sort * per_seg;
+    p.hist_done = d->hist_done ? 1 : 0;
     g.blk_off[0] = 0;
     for (int s = 0; s < ns; ++s) g.blk_off[s + 1] = g.blk_off[s] + (int)(((long)d->B * p.seg.n[s] + kThreads * 4 - 1) / (kThreads * 4));
-    g.nbins = (long)ns * d->B * g.tiles * 128;
+    g.nbins = (long)nslots_sort * per_seg;
     g.bins = (int *)d->sort_bins; g.sums = (int *)d->sort_sums;
     g.rec = (float4 *)d->sorted_ev;
     build_bands(p, (long)d->B * p.nslots * 4 * p.ig.plane * 8);

@@ -20,40 +20,57 @@ __global__ void __launch_bounds__(kThreads) stage_events_kernel(float4 *__restri
     mk_out[i] = mk_in[i];
 }
 
-// both event sets of one pass in one launch: CTAs [0, nb0) stage set 0, the rest set 1
+// both event sets of one pass in one launch: CTAs [0, nb0) stage set 0, the rest set 1.  With `bins` the kernel also
+// counts every non-padding row into the tile-sort histogram of its segment (what sort_hist_kernel would do in the
+// forward call, there at the price of another pass over the events).
 struct StageTwo {
     float4 *ev_io[2]; const float2 *mk_in[2]; float4 *ev_out[2]; float2 *mk_out[2];
     long rows[2]; float pass_index[2]; const float *ts_override[2]; int nb0;
+    int *bins; int first_bin[2]; int n[2]; int tiles_x, tiles, H, W;
 };
-__global__ void __launch_bounds__(kThreads) stage_two_kernel(const __grid_constant__ StageTwo s) {
-    const int k = blockIdx.x >= s.nb0 ? 1 : 0;
-    const long i = (long)(blockIdx.x - (k ? s.nb0 : 0)) * kThreads + threadIdx.x;
+__device__ __forceinline__ void stage_two_body(const StageTwo &s, int blk) {
+    const int k = blk >= s.nb0 ? 1 : 0;
+    const long i = (long)(blk - (k ? s.nb0 : 0)) * kThreads + threadIdx.x;
     if (i >= s.rows[k]) return;
     float4 e = s.ev_io[k][i];
     e.x = e.x + s.pass_index[k];
     s.ev_io[k][i] = e;
     if (s.ts_override[k]) e.x = __ldg(s.ts_override[k]);
     s.ev_out[k][i] = e;
-    s.mk_out[k][i] = s.mk_in[k][i];
+    const float2 m = s.mk_in[k][i];
+    s.mk_out[k][i] = m;
+    if (s.bins && !(m.x == 0.0f && m.y == 0.0f))
+        atomicAdd(s.bins + sort_bin(s.first_bin[k], s.tiles_x, s.tiles, s.H, s.W, (int)(i / s.n[k]), e.y, e.z), 1);
 }
-
 struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
 
-// [B][2][H][W] planar (ch0 = x, ch1 = y) -> dual-phase float2 [B][phase][H+1][Wp] with zero padding (tef_device.cuh)
-__global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_constant__ FlowPtrs src, float2 *__restrict__ packed, int t, int P,
-                                                             int B, Res r) {
-    const int f = blockIdx.z, b = blockIdx.y;
+// [B][2][H][W] planar (ch0 = x, ch1 = y) -> dual-phase float2 [B][phase][H+1][Wp] with zero padding (tef_device.cuh);
+// bx CTAs walk one (flow scale f, sample b) map
+__device__ __forceinline__ void pack_flow_body(const FlowPtrs &src, float2 *__restrict__ packed, int t, int P, int B, const Res &r,
+                                               int f, int b, int xblk, int bx) {
     const long HW = (long)r.H * r.W;
     const float *sx = src.p[f] + (long)b * 2 * HW, *sy = sx + HW;
     float2 *dst = packed + (((long)f * P + t) * B + b) * 2 * r.fplane;
     const int n = 2 * r.fplane;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    for (int i = xblk * kThreads + threadIdx.x; i < n; i += bx * kThreads) {
         const int phase = i >= r.fplane;
         const int q = i - phase * r.fplane;
         const int y = q / r.Wp, x = q % r.Wp - phase;
         const bool in = (y < r.H) && (x >= 0) && (x < r.W);
         dst[i] = in ? make_float2(sx[y * r.W + x], sy[y * r.W + x]) : make_float2(0.f, 0.f);
     }
+}
+__global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_constant__ FlowPtrs src, float2 *__restrict__ packed, int t, int P,
+                                                             int B, Res r) {
+    pack_flow_body(src, packed, t, P, B, r, blockIdx.z, blockIdx.y, blockIdx.x, gridDim.x);
+}
+
+// Iterative.update / Linear.update in ONE launch: CTAs [0, nb_stage) stage (and count) the events, the rest pack the flow maps
+struct PackArgs { FlowPtrs src; float2 *packed; int t, P, B, F, bx; Res r; };
+__global__ void __launch_bounds__(kThreads) update_pass_kernel(const __grid_constant__ StageTwo s, const __grid_constant__ PackArgs k, int nb_stage) {
+    if ((int)blockIdx.x < nb_stage) { stage_two_body(s, blockIdx.x); return; }
+    const int pb = blockIdx.x - nb_stage;
+    pack_flow_body(k.src, k.packed, k.t, k.P, k.B, k.r, pb / (k.bx * k.B), (pb / k.bx) % k.B, pb % k.bx, k.bx);
 }
 
 template <bool DET>
@@ -117,23 +134,44 @@ extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P,
 
 extern "C" int tef_update_pass(const tef_update_desc *u, void *stream) {
     if (!u) return TEF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    PackArgs k;
+    k.F = 0; k.bx = 0; k.B = u->B;
     if (u->F > 0) {
-        int rc = tef_pack_flow(u->flow_maps, u->F, u->t, u->P, u->B, u->H, u->W, u->packed, stream);
-        if (rc) return rc;
+        if (!u->packed || u->F > TEF_MAX_FLOWS || u->t < 0 || u->t >= u->P || u->B < 1) return TEF_EINVAL;
+        for (int f = 0; f < u->F; ++f) { if (!u->flow_maps[f]) return TEF_EINVAL; k.src.p[f] = (const float *)u->flow_maps[f]; }
+        k.packed = (float2 *)u->packed; k.t = u->t; k.P = u->P; k.F = u->F; k.r = Res::make(u->H, u->W);
+        k.bx = (2 * k.r.fplane + kThreads - 1) / kThreads;
+        if (k.bx > 148 * 4) k.bx = 148 * 4;
     }
     StageTwo s;
-    for (int k = 0; k < 2; ++k) {
-        if (u->rows[k] < 0) return TEF_EINVAL;
-        if (u->rows[k] > 0 && (!u->events[k] || !u->masks[k] || !u->ev_out[k] || !u->mk_out[k])) return TEF_EINVAL;
-        s.ev_io[k] = (float4 *)u->events[k]; s.mk_in[k] = (const float2 *)u->masks[k];
-        s.ev_out[k] = (float4 *)u->ev_out[k]; s.mk_out[k] = (float2 *)u->mk_out[k];
-        s.rows[k] = u->rows[k]; s.pass_index[k] = u->pass_index[k]; s.ts_override[k] = u->ts_override[k];
+    for (int i = 0; i < 2; ++i) {
+        if (u->rows[i] < 0) return TEF_EINVAL;
+        if (u->rows[i] > 0 && (!u->events[i] || !u->masks[i] || !u->ev_out[i] || !u->mk_out[i])) return TEF_EINVAL;
+        s.ev_io[i] = (float4 *)u->events[i]; s.mk_in[i] = (const float2 *)u->masks[i];
+        s.ev_out[i] = (float4 *)u->ev_out[i]; s.mk_out[i] = (float2 *)u->mk_out[i];
+        s.rows[i] = u->rows[i]; s.pass_index[i] = u->pass_index[i]; s.ts_override[i] = u->ts_override[i];
+    }
+    s.bins = nullptr;
+    if (u->hist) {
+        if (!u->sort_bins || u->t < 0 || u->t >= u->P || u->B < 1) return TEF_EINVAL;
+        s.tiles_x = (u->W + 15) / 16; s.tiles = s.tiles_x * ((u->H + 7) / 8); s.H = u->H; s.W = u->W;
+        const long per_seg = (long)u->B * s.tiles * 128;
+        if (2 * u->P * per_seg > 0x7fffffffl) return TEF_ELIMIT;
+        if (u->zero_bins) cudaMemsetAsync(u->sort_bins, 0, sizeof(int) * (2 * u->P * per_seg + 1), st);
+        s.bins = (int *)u->sort_bins;
+        for (int i = 0; i < 2; ++i) {
+            if (u->rows[i] % u->B) return TEF_EINVAL;
+            s.first_bin[i] = (int)((i * u->P + u->t) * per_seg);
+            s.n[i] = (int)(u->rows[i] / u->B) > 0 ? (int)(u->rows[i] / u->B) : 1;
+        }
     }
     s.nb0 = (int)((u->rows[0] + kThreads - 1) / kThreads);
     const int nb = s.nb0 + (int)((u->rows[1] + kThreads - 1) / kThreads);
-    if (nb > 0) {
-        ProfScope ps(K_STAGE_EVENTS, (cudaStream_t)stream);
-        stage_two_kernel<<<nb, kThreads, 0, (cudaStream_t)stream>>>(s);
+    const int npk = k.bx * k.B * k.F;
+    if (nb + npk > 0) {
+        ProfScope ps(K_STAGE_EVENTS, st);                  // one launch: staging (+ histogram) and flow packing
+        update_pass_kernel<<<nb + npk, kThreads, 0, st>>>(s, k, nb);
     }
     return (int)cudaGetLastError();
 }

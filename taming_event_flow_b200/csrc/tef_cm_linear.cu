@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_kernel(const __grid_const
 }
 
 template <bool DET>
-__global__ void __launch_bounds__(kThreads) linear_bwd_kernel(const __grid_constant__ CmParams p) {
+__global__ void __launch_bounds__(kThreads, 4) linear_bwd_kernel(const __grid_constant__ CmParams p) {
     int t, b, row, set; float4 e; float2 m;
     if (!locate_sorted(p, t, b, e, m, row, set)) return;
     const int f = blockIdx.y;

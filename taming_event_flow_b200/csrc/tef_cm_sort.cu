@@ -7,19 +7,16 @@
 // makes the lanes of a warp start from the same few pixels and, the flow being smooth, stay neighbours
 // along the whole warping chain.  Padding rows (mask 0,0) are dropped on the way.
 //
-// Three steps, all inside tef_*_forward:  histogram over per-pixel bins (1 L2 atomic per event),
-// exclusive scan of the bins, scatter (1 returning atomic per event).  Output rows are 32-byte records
+// Three steps: histogram over per-pixel bins (1 L2 atomic per event; fused into tef_update_pass when the descriptor says
+// hist_done, otherwise done here), exclusive scan of the bins, scatter (1 returning atomic per event).  Output rows are 32-byte records
 // (ts, y, x, sample index | mask+, mask-, 0, 0): the polarity column is not needed by the loss, the mask carries it.
 #include "tef_cm_common.cuh"
 #include "tef_prof.cuh"
 
 namespace tef {
 
-__device__ __forceinline__ int bin_of(const SortGeom &g, int seg, int b, float y, float x) {
-    int iy = (int)fminf(fmaxf(floorf(y), 0.0f), (float)(g.H - 1));
-    int ix = (int)fminf(fmaxf(floorf(x), 0.0f), (float)(g.W - 1));
-    const int tile = (iy >> 3) * g.tiles_x + (ix >> 4);
-    return ((seg * g.B + b) * g.tiles + tile) * 128 + ((iy & 7) << 4) + (ix & 15);
+__device__ __forceinline__ int bin_of(const CmParams &p, int seg, int b, float y, float x) {
+    return sort_bin(p.seg.first_bin[seg], p.sort.tiles_x, p.sort.tiles, p.sort.H, p.sort.W, b, y, x);
 }
 
 // Both kernels walk a segment with kSortIlp rows per thread (strided by the CTA size, so every access stays
@@ -52,7 +49,7 @@ __global__ void __launch_bounds__(kThreads) sort_hist_kernel(const __grid_consta
 #pragma unroll
     for (int k = 0; k < kSortIlp; ++k) {
         if (m[k].x == 0.0f && m[k].y == 0.0f) continue;            // padding rows are dropped
-        atomicAdd(p.sort.bins + bin_of(p.sort, sg, (int)(row[k] / n), e[k].y, e[k].z), 1);
+        atomicAdd(p.sort.bins + bin_of(p, sg, (int)(row[k] / n), e[k].y, e[k].z), 1);
     }
 }
 
@@ -71,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const __grid_con
         dst[k] = -1;
         if (m[k].x == 0.0f && m[k].y == 0.0f) continue;
         const int b = (int)(row[k] / n);
-        dst[k] = atomicAdd(p.sort.bins + bin_of(p.sort, sg, b, e[k].y, e[k].z), 1);
+        dst[k] = atomicAdd(p.sort.bins + bin_of(p, sg, b, e[k].y, e[k].z), 1);
         e[k].w = __int_as_float(b);
     }
     // one 256-bit store per event (STG.E.ENL2.256): a full, aligned 32-byte sector, so the scattered writes never
@@ -151,10 +148,10 @@ int tef_sort_events(const CmParams &p, cudaStream_t st) {
     const int nblk = p.sort.blk_off[p.seg.nseg];
     const long nbins = p.sort.nbins;
     if (!p.sort.bins || !p.sort.sums || (nblk > 0 && !p.sort.rec)) return TEF_EINVAL;
-    cudaMemsetAsync(p.sort.bins, 0, sizeof(int) * (nbins + 1), st);
+    if (!p.hist_done) cudaMemsetAsync(p.sort.bins, 0, sizeof(int) * (nbins + 1), st);     // else counted by tef_update_pass
     if (nblk == 0) return (int)cudaGetLastError();
     const int nchunks = (int)((nbins + kScanChunk - 1) / kScanChunk);
-    { ProfScope ps(K_SORT_HIST, st); sort_hist_kernel<<<nblk, kThreads, 0, st>>>(p); }
+    if (!p.hist_done) { ProfScope ps(K_SORT_HIST, st); sort_hist_kernel<<<nblk, kThreads, 0, st>>>(p); }
     { ProfScope ps(K_SORT_SCAN, st); scan_sums_kernel<<<nchunks, kThreads, 0, st>>>(p.sort.bins, p.sort.sums, nbins); }
     { ProfScope ps(K_SORT_SCAN, st); scan_top_kernel<<<1, kThreads, 0, st>>>(p.sort.sums, nchunks); }
     { ProfScope ps(K_SORT_SCAN, st); scan_apply_kernel<<<nchunks, kThreads, 0, st>>>(p.sort.bins, p.sort.sums, nbins); }

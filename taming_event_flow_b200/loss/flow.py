@@ -11,6 +11,7 @@ The returned loss is a 0-dim tensor wired into autograd: ``loss.backward()`` del
 gradients to every tensor of every ``flow_list`` handed to `update`.
 """
 import ctypes
+import os
 
 import torch
 
@@ -18,6 +19,10 @@ from .. import _lib
 from .._lib import CmDesc, check, lib, ptr, require_cuda, stream
 
 _MODES = {"one": 1, "two": 2, "four": 4}
+
+
+# TEF_FUSED_HIST=0: build the tile-sort histogram inside the forward call instead of inside update() (A/B switch)
+_FUSED_HIST = os.environ.get("TEF_FUSED_HIST", "1") != "0"
 
 
 class _Workspace:
@@ -55,6 +60,7 @@ class _Window:
         self.img = None
         self.den = None
         self.consumed = False
+        self.hist_valid = False    # sort_bins holds the fused histogram of every pass given to update() so far
 
     def release(self):
         """Hand the workspace back (after backward, or when the window dies un-differentiated)."""
@@ -254,6 +260,12 @@ class BaseEventWarping(torch.nn.Module):
             # passes beyond the loss window are not part of the loss (upstream never reads them); only the in-place
             # timestamp update is observable, so stage into the scratch rows and skip the packing slot
             u.F = 0
+        elif _FUSED_HIST and (t == 0 or w.hist_valid):
+            # the staging kernel also counts the events into the tile-sort histogram (saves the forward a pass over them)
+            tiles = ((W + 15) // 16) * ((H + 7) // 8)
+            bins = w.ws.get("bins", (2 * P * B * tiles * 128 + 1,), torch.int32, dev)
+            u.sort_bins, u.hist, u.zero_bins = bins.data_ptr(), 1, int(t == 0)
+            w.hist_valid = True
         check(self._fn_update(ctypes.byref(u), stream()), "tef_update_pass")
 
     # ---------------------------------------------------------------- kernels
@@ -273,6 +285,7 @@ class BaseEventWarping(torch.nn.Module):
                 d.mk[k][t] = w.mk[k][t]
                 d.n[k][t] = w.n[k][t]
         d.flow = w.packed.data_ptr()
+        d.hist_done = int(w.hist_valid)
         return d
 
     def _forward_kernels(self, w):
@@ -299,6 +312,7 @@ class BaseEventWarping(torch.nn.Module):
         d.acc_sum, d.acc_nnz, d.loss = w.acc_sum.data_ptr(), w.acc_nnz.data_ptr(), loss.data_ptr()
         fn = lib().tef_linear_forward if self._linear else lib().tef_iterative_forward
         check(fn(ctypes.byref(d), stream()), "tef_linear_forward" if self._linear else "tef_iterative_forward")
+        w.hist_valid = False       # the scan turned the counts into offsets: a second forward() counts again by itself
         w.consumed = False
         return loss.view(())
 

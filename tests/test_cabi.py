@@ -29,7 +29,7 @@ def test_descriptor_layout_matches_header():
     from taming_event_flow_b200 import _lib
 
     # 10 ints, then 2x31 pointers x2, 2x31 ints, 14 pointers
-    expect = 10 * 4 + 2 * 31 * 8 * 2 + 2 * 31 * 4 + 14 * 8
+    expect = 10 * 4 + 2 * 31 * 8 * 2 + 2 * 31 * 4 + 14 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.CmDesc) == expect
     lib = ctypes.CDLL(_lib.LIB_PATH)
     d = _lib.CmDesc()

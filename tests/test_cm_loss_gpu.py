@@ -294,3 +294,32 @@ def test_non_contiguous_inputs_are_handled():
     g = np.stack([np.stack([flows[t][f].grad.cpu().numpy() for t in range(P)]) for f in range(2)])
     assert abs(loss.item() - ref["loss"]) <= 1e-6 * abs(ref["loss"])
     assert rel_err(g, ref["gflow"])[0] < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["iterative", "linear"])
+def test_fused_histogram_equals_forward_histogram_and_forward_twice(kind, monkeypatch):
+    """update() counts the events into the tile-sort histogram (fused into the staging kernel); the library can also do it
+    inside the forward call (descriptor hist_done = 0).  Same sorted order up to ties, same loss; a second forward() on
+    the same window (whose histogram the first call consumed) must count again by itself."""
+    from taming_event_flow_b200.loss import flow as tef_flow
+
+    B, P, N, Nd, H, W, F = 3, 6, 1500, 700, 40, 56, 2
+    seq = syn.make_sequence(5, B, P, N, Nd, H, W, F, 3.0, True, "uniform")
+    cfg = syn.loss_config(H, W, B, P, 1, "two")
+    cfg["loss"]["deterministic"] = True                      # order-independent sums: the two routes must agree bit for bit
+    out = {}
+    for fused in (True, False):
+        monkeypatch.setattr(tef_flow, "_FUSED_HIST", fused)
+        m = (tef_flow.Iterative if kind == "iterative" else tef_flow.Linear)(copy.deepcopy(cfg), torch.device("cuda"))
+        flows = [[f.cuda().requires_grad_(True) for f in per] for per in seq["flows"]]
+        for t in range(P):
+            m.update(flows[t], seq["events"][t].cuda(), seq["masks"][t].cuda(), seq["d_events"][t].cuda(), seq["d_masks"][t].cuda())
+        assert m._win.hist_valid == fused
+        with torch.no_grad():
+            first = m().item()
+        assert not m._win.hist_valid
+        loss = m()                                           # second forward on the same window
+        loss.backward()
+        out[fused] = (first, loss.item(), torch.stack([f.grad for per in flows for f in per]).cpu())
+    assert out[True][0] == out[True][1] == out[False][0] == out[False][1]
+    assert torch.equal(out[True][2], out[False][2])
