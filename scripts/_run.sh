@@ -1,4 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-for wl in iterative_480x640_1Mev iterative_128x128_b8_f4 iterative_128x128_b8_f1 iterative_480x640_100kev linear_480x640_1Mev; do
-  python scripts/kernel_times.py --workload $wl 2>&1 | tail -1 | cut -c1-340
-done
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1i.json 2> gpurun_out/bench_r1i.err; tail -c 300 gpurun_out/bench_r1i.err

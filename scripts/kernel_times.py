@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--workload", default=bench.DEFAULT_WORKLOAD)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--events", type=int, default=None)
+    ap.add_argument("--no-prof", action="store_true", help="time the steps without the library's per-kernel CUDA events")
     args = ap.parse_args()
     from taming_event_flow_b200 import _lib, synthetic as syn
     from taming_event_flow_b200.loss import flow as tef_flow
@@ -51,7 +52,7 @@ def main():
         step(i)
     torch.cuda.synchronize()
     L.tef_prof_reset()
-    L.tef_prof_enable(1)
+    L.tef_prof_enable(0 if args.no_prof else 1)
     t0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(2 + i)
