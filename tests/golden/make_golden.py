@@ -212,21 +212,25 @@ def make_encoding_cases():
 
 
 def make_flow_val_cases():
-    """loss/flow_val.py (first "next" row of SURVEY.md §8f): Linear and Iterative validation on a synthetic 5-window sequence."""
+    """loss/flow_val.py (first "next" row of SURVEY.md §8f): Linear and Iterative validation on synthetic window sequences."""
+    _flow_val_case("flow_val.npz", 40, 56, 5, 1200, 2.0, 8, False, 77)
+    _flow_val_case("flow_val_b.npz", 37, 53, 4, 500, 4.0, 4, True, 78)      # odd resolution, larger flow, round_ts
+
+
+def _flow_val_case(fname, H, W, P, N, sigma, coarse, round_ts, seed):
     from loss import flow_val as ref_val
 
-    H, W, P, N = 40, 56, 5, 1200
-    gen = torch.Generator().manual_seed(77)
-    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
+    gen = torch.Generator().manual_seed(seed)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": round_ts}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
     wins = []
     for t in range(P):
         ev, mk = syn.make_window(gen, 1, N, H, W)
-        flow = syn.make_flow(gen, 1, H, W, 2.0, coarse=8)
+        flow = syn.make_flow(gen, 1, H, W, sigma, coarse=coarse)
         emask = (torch.rand(1, 1, H, W, generator=gen) > 0.3).float()
         wins.append((ev, mk, flow, emask))
-    gt = syn.make_flow(gen, 1, H, W, 2.0, coarse=8)
+    gt = syn.make_flow(gen, 1, H, W, sigma, coarse=coarse)
     gt[:, :, :5] = 0.0                                                    # pixels without ground truth
-    out = {"H": H, "W": W, "P": P, "gt": gt.numpy()}
+    out = {"H": H, "W": W, "P": P, "gt": gt.numpy(), "round_ts": int(round_ts)}
     for t, (ev, mk, flow, emask) in enumerate(wins):
         out["ev%d" % t], out["mk%d" % t], out["flow%d" % t], out["emask%d" % t] = ev.numpy(), mk.numpy(), flow.numpy(), emask.numpy()
     for name, cls in (("linear", ref_val.Linear), ("iterative", ref_val.Iterative)):
@@ -249,8 +253,8 @@ def make_flow_val_cases():
                         out[key + "iwe_%s_%d" % (mode, ri)] = m.window_iwe(mode=mode, round_idx=ri).numpy()
         m.reset()
         assert m.num_passes == 0
-    np.savez_compressed(os.path.join(HERE, "flow_val.npz"), **out)
-    print("flow_val cases written")
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+    print("flow_val case written:", fname)
 
 
 def make_smoothness_cases():

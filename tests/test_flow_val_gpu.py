@@ -14,13 +14,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+@pytest.mark.parametrize("fixture", ["flow_val.npz", "flow_val_b.npz"])
 @pytest.mark.parametrize("name", ["linear", "iterative"])
-def test_flow_val_golden(name):
+def test_flow_val_golden(name, fixture):
     from taming_event_flow_b200.loss import flow_val as fv
 
-    z = np.load(os.path.join(GOLDEN, "flow_val.npz"))
+    z = np.load(os.path.join(GOLDEN, fixture))
     H, W, P = int(z["H"]), int(z["W"]), int(z["P"])
-    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": False}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
+    round_ts = bool(int(z["round_ts"])) if "round_ts" in z.files else False
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"round_ts": round_ts}, "vis": {"mask_output": True}, "metrics": {"name": ["AEE"]}}
     m = (fv.Linear if name == "linear" else fv.Iterative)(copy.deepcopy(cfg), "cuda")
     gt = torch.tensor(z["gt"]).cuda()
     checked = 0
