@@ -32,8 +32,12 @@ class _Workspace:
 
     def __init__(self):
         self.bufs = {}
+        self.views = {}        # (key, shape) -> view of the current buffer: steady-state windows ask for the same shapes
 
     def get(self, key, shape, dtype, device):
+        hit = self.views.get((key, shape))
+        if hit is not None and hit.dtype == dtype and hit.device == device:
+            return hit
         n = 1
         for d in shape:
             n *= int(d)
@@ -41,7 +45,12 @@ class _Workspace:
         if buf is None or buf.numel() < n or buf.dtype != dtype or buf.device != device:
             buf = torch.empty((max(n, 1),), dtype=dtype, device=device)
             self.bufs[key] = buf
-        return buf[:n].view(shape)
+            self.views = {k: v for k, v in self.views.items() if k[0] != key}     # views of the old buffer are stale
+        view = buf[:n].view(shape)
+        if len(self.views) > 512:                   # ragged windows ask for ever-changing shapes: keep the cache bounded
+            self.views.clear()
+        self.views[(key, shape)] = view
+        return view
 
 
 class _Window:
@@ -61,6 +70,7 @@ class _Window:
         self.den = None
         self.consumed = False
         self.hist_valid = False    # sort_bins holds the fused histogram of every pass given to update() so far
+        self.desc = None           # descriptor of the last forward call, reused by backward
 
     def release(self):
         """Hand the workspace back (after backward, or when the window dies un-differentiated)."""
@@ -89,11 +99,9 @@ class _CMLoss(torch.autograd.Function):
     def backward(ctx, gout):
         grads = ctx.module._backward_kernels(ctx.window, gout)     # [P,F,B,2,H,W]
         P, F = grads.shape[0], grads.shape[1]
-        out = []
-        for t in range(len(ctx.window.flows)):
-            for f in range(F):
-                out.append(grads[t, f] if t < P else None)
-        return (None, None) + tuple(out)
+        out = grads.view((P * F,) + grads.shape[2:]).unbind(0)     # one call instead of P*F Python-level slices
+        extra = (len(ctx.window.flows) - P) * F                    # passes beyond the loss window get no gradient
+        return (None, None) + out + (None,) * extra
 
 
 class _Smoothness(torch.autograd.Function):
@@ -313,6 +321,8 @@ class BaseEventWarping(torch.nn.Module):
         fn = lib().tef_linear_forward if self._linear else lib().tef_iterative_forward
         check(fn(ctypes.byref(d), stream()), "tef_linear_forward" if self._linear else "tef_iterative_forward")
         w.hist_valid = False       # the scan turned the counts into offsets: a second forward() counts again by itself
+        d.hist_done = 0
+        w.desc = d
         w.consumed = False
         return loss.view(())
 
@@ -326,7 +336,7 @@ class BaseEventWarping(torch.nn.Module):
             raise RuntimeError("the CM loss graph has already been back-propagated (the image buffers are reused in place)")
         F, B, H, W = w.shape
         P = self._max_passes()
-        d = self._desc(w)
+        d = w.desc if w.desc is not None else self._desc(w)          # the descriptor of the forward call (same workspace)
         dev = w.packed.device
         gpacked = w.ws.get("gpacked", (w.n_gflow,), torch.float32, dev)
         grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)     # handed to autograd: not pooled
