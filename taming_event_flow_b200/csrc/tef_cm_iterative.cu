@@ -41,7 +41,8 @@ namespace tef {
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
                                                int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */,
-                                               float2 *__restrict__ pb /* this row of posbuf (stride rows_grad) or nullptr */) {
+                                               float2 *__restrict__ pb /* this row of posbuf (stride rows_grad) or nullptr */,
+                                               int keep_lo, int keep_hi /* nodes some scale splats for this pass; the others only feed the mask */) {
     const long stride = (long)p.B * 2 * p.res.fplane;   // one pass further (dual-phase maps)
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
@@ -60,8 +61,10 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
             safe = true;
         }
         tprev = (float)tr;
-        *pw = make_float2(y, x);
-        if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));   // coalesced streaming store (evict-first), kept for the backward kernel
+        if (tr <= keep_hi) {
+            *pw = make_float2(y, x);
+            if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));   // coalesced streaming store (evict-first), kept for the backward kernel
+        }
     }
     y = y0; x = x0; tprev = ts; al = true; safe = in0;
     map = flow_fb + (long)t * stride;
@@ -76,8 +79,10 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
             safe = true;
         }
         tprev = (float)tr;
-        *pw = make_float2(y, x);
-        if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));
+        if (tr >= keep_lo) {
+            *pw = make_float2(y, x);
+            if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));
+        }
     }
     return alive;
 }
@@ -129,7 +134,11 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
 
     // gradient-carrying rows keep their chain for the backward kernel
     float2 *pb = (set == 0 && p.posbuf) ? p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row : nullptr;
-    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb);
+    // nodes that any scale splats for this pass (uniform per CTA): only those are kept, on chip and for the backward kernel
+    int keep_lo = p.P + 1, keep_hi = -1;
+    for (int s = 0; s < p.sc.S; ++s)
+        if (sw[s].valid) { keep_lo = min(keep_lo, sw[s].tr0); keep_hi = max(keep_hi, sw[s].tr1); }
+    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb, keep_lo, keep_hi);
     if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
 
     const uint32_t has = active_scales(p, sw, alive);
