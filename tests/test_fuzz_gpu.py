@@ -64,3 +64,32 @@ def test_random_configuration(seed):
         assert linf < TOL and l2 < TOL, (c, "grad", linf, l2)
     else:
         assert not g.any()
+
+
+@pytest.mark.parametrize("N,Nd", [(0, 50), (0, 0), (1, 0), (0, 1)])
+def test_empty_event_lists(N, Nd):
+    """No gradient-carrying events (or no events at all): the reference returns the detached events' loss (or 0) and zero
+    gradients; so must the kernels, without touching empty buffers."""
+    B, P, H, W, F = 2, 4, 16, 20, 1
+    seq = syn.make_sequence(3, B, P, max(N, 1), max(Nd, 1), H, W, F, 2.0, False, "uniform")
+    if N == 0:
+        seq["events"], seq["masks"] = [e[:, :0] for e in seq["events"]], [m[:, :0] for m in seq["masks"]]
+    if Nd == 0:
+        seq["d_events"], seq["d_masks"] = [e[:, :0] for e in seq["d_events"]], [m[:, :0] for m in seq["d_masks"]]
+    o = orc.iterative(orc.make_cfg(B, H, W, P, F, 1, "two", True), seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"],
+                      np.float32, want_grad=True, want_iwe=True)
+    for kind in (tef_flow.Iterative, tef_flow.Linear):
+        m = kind(syn.loss_config(H, W, B, P, 1, "two", warping=kind.__name__), torch.device("cuda"))
+        flows = [[f.cuda().requires_grad_(True) for f in per] for per in seq["flows"]]
+        for t in range(P):
+            m.update(flows[t], seq["events"][t].cuda().clone(), seq["masks"][t].cuda(), seq["d_events"][t].cuda().clone(), seq["d_masks"][t].cuda())
+        loss = m()
+        loss.backward()
+        g = torch.stack([f.grad for per in flows for f in per])
+        assert torch.isfinite(loss) and torch.isfinite(g).all()
+        if kind is tef_flow.Iterative:
+            assert abs(loss.item() - o["loss"]) <= TOL * max(abs(o["loss"]), 1e-6)
+            linf = np.abs(g.cpu().numpy().reshape(o["gflow"].shape) - o["gflow"]).max()
+            assert linf <= TOL * max(np.abs(o["gflow"]).max(), 1e-12)
+        if N == 0:
+            assert not g.any()
