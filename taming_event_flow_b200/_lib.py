@@ -29,6 +29,11 @@ class TefError(RuntimeError):
     pass
 
 
+class EmptyWindowError(RuntimeError, ValueError):
+    """A temporal scale has no window to concatenate.  The reference fails in ``torch.cat([])`` (loss/flow.py:689), which
+    raises RuntimeError up to torch 2.x and ValueError in recent releases (2.11 here): this one is caught by either."""
+
+
 class CmDesc(ctypes.Structure):
     """Mirror of ``tef_cm_desc``."""
     _fields_ = (
@@ -126,7 +131,7 @@ def check(rc, what):
     if rc != 0:
         msg = lib().tef_strerror(int(rc)).decode()
         if rc == -3:
-            raise RuntimeError("%s: %s" % (what, msg))     # reference: RuntimeError from torch.cat([])
+            raise EmptyWindowError("%s: %s" % (what, msg))  # reference: torch.cat([]) fails
         if rc == -4:
             raise TypeError("%s: %s" % (what, msg))        # reference: TypeError (None in torch.cat)
         raise TefError("%s failed: %s (code %d)" % (what, msg, rc))
