@@ -71,7 +71,7 @@ def test_random_primitives(seed):
 def test_random_encodings_and_deblur(seed):
     r = np.random.default_rng(500 + seed)
     H, W, n, bins = int(r.integers(1, 50)), int(r.integers(1, 70)), int(r.integers(0, 3000)), int(r.integers(1, 8))
-    xs = r.integers(0, W, n).astype(np.float32) + (r.random(n) < 0.1) * 0.6        # .long() truncation
+    xs = (r.integers(0, W, n) + (r.random(n) < 0.1) * 0.6).astype(np.float32)      # .long() truncation
     ys = r.integers(0, H, n).astype(np.float32)
     ts = np.sort(r.random(n)).astype(np.float32)
     ps = (r.integers(0, 2, n) * 2 - 1).astype(np.float32)
