@@ -96,3 +96,30 @@ def test_priors_without_grad_and_in_the_total_loss():
     cm = m2()
     want = cm.item() + 0.5 * s.item() + 2.0 * t.item()
     assert abs(total.item() - want) <= TOL * abs(want)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_priors_random_shapes(seed):
+    """Odd resolutions, 1-3 flow scales, 2-6 passes, small and large flows: values against the numpy oracle, gradients
+    against a central finite difference of the oracle in fp64 along a random direction."""
+    r = np.random.default_rng(70 + seed)
+    B, P, F = int(r.integers(1, 4)), int(r.integers(2, 7)), int(r.integers(1, 4))
+    H, W = int(r.integers(3, 45)), int(r.integers(3, 60))
+    sigma = float(r.choice([0.5, 3.0, 8.0]))
+    flows_np = [[r.normal(0, sigma, (B, 2, H, W)).astype(np.float32) for _ in range(F)] for _ in range(P)]
+    m, flows = _module("Iterative" if seed % 2 == 0 else "Linear", B, P, H, W, flows_np)
+    for fn, orc_fn in ((m.flow_spatial_smoothing, so.flow_spatial_smoothing), (m.flow_temporal_smoothing, so.flow_temporal_smoothing)):
+        for per in flows:
+            for f in per:
+                f.grad = None
+        val = fn()
+        ref = orc_fn(flows_np)
+        assert abs(val.item() - ref) <= TOL * abs(ref), (val.item(), ref)
+        val.backward()
+        d = [[r.normal(0, 1, (B, 2, H, W)) for _ in range(F)] for _ in range(P)]
+        h = 1e-6
+        plus = [[flows_np[t][f].astype(np.float64) + h * d[t][f] for f in range(F)] for t in range(P)]
+        minus = [[flows_np[t][f].astype(np.float64) - h * d[t][f] for f in range(F)] for t in range(P)]
+        fd = (orc_fn(plus) - orc_fn(minus)) / (2 * h)
+        an = sum(float((flows[t][f].grad.double().cpu().numpy() * d[t][f]).sum()) for t in range(P) for f in range(F))
+        assert abs(an - fd) <= 5e-4 * max(abs(fd), 1e-3), (an, fd)
