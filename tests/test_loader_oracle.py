@@ -80,3 +80,45 @@ def test_device_functions_refuse_cpu_tensors():
         tef_base.create_polarity_mask(torch.ones(4))
     with pytest.raises(RuntimeError):
         tef_base.format_windows([np.zeros(0, np.uint64)], (4, 4), "cpu")
+
+
+REF = os.environ.get("TEF_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dataloader")), reason="reference not mounted")
+@pytest.mark.parametrize("seed", range(10))
+def test_loader_oracle_matches_live_reference(seed):
+    """Random ragged batches against the unmodified BaseDataLoader static methods imported live (build container only)."""
+    import types
+    import warnings
+
+    import torch
+
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    warnings.filterwarnings("ignore")
+    from dataloader.base import BaseDataLoader  # reference
+    from dataloader.encodings import events_to_channels  # reference
+
+    r = np.random.default_rng(600 + seed)
+    H, W = int(r.integers(2, 50)), int(r.integers(2, 70))
+    me = types.SimpleNamespace(device=torch.device("cpu"))
+    wins, batch = [], []
+    for _ in range(int(r.integers(1, 5))):
+        n = int(r.integers(0, 400))
+        xs, ys = r.integers(0, W, n), r.integers(0, H, n)
+        ts, ps = np.sort(r.uniform(1e3, 9e5, n)), r.integers(0, 2, n)
+        wins.append((xs, ys, ts, ps))
+        fx, fy, ft, fp = BaseDataLoader.event_formatting(me, xs, ys, ts, ps)
+        ev, mk = BaseDataLoader.create_list_encoding(fx, fy, ft, fp), BaseDataLoader.create_polarity_mask(fp)
+        batch.append({"event_list": ev, "event_list_pol_mask": mk, "event_cnt": events_to_channels(fx, fy, fp, sensor_size=(H, W))})
+        packed = tef_base.pack_events(xs, ys, ts, ps)
+        ux, uy, ut, up = lo.unpack_events(packed)
+        assert np.array_equal(ux, xs) and np.array_equal(uy, ys) and np.array_equal(up, ps) and same_bits(ut, ts.astype(np.float32))
+    want = BaseDataLoader.custom_collate(batch)
+    got = lo.format_windows(wins, (H, W))
+    for k in ("event_list", "event_list_pol_mask", "event_cnt"):
+        a, b = got[k], want[k].numpy()
+        assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(a)
+        assert np.array_equal(a.view(np.uint32)[ok], b.view(np.uint32)[ok]), k
