@@ -147,3 +147,33 @@ def test_format_windows_ragged_split_feeds_the_loss():
                            torch.zeros((B, 0, 4), device="cuda"), torch.zeros((B, 0, 2), device="cuda"))
         losses.append(mod().item())
     assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_format_windows_random_ragged_batches(seed):
+    r = np.random.default_rng(800 + seed)
+    H, W, B = int(r.integers(2, 60)), int(r.integers(2, 80)), int(r.integers(1, 6))
+    wins = []
+    for _ in range(B):
+        n = int(r.choice([0, 1, 2, int(r.integers(3, 600))]))
+        wins.append((r.integers(0, W, n), r.integers(0, H, n), np.sort(r.uniform(1e3, 9e5, n)), r.integers(0, 2, n)))
+    want = lo.format_windows(wins, (H, W))
+    packed = [tef_base.pack_events(*w) for w in wins]
+    got = tef_base.format_windows(packed, (H, W), "cuda")
+    for key in ("event_list", "event_list_pol_mask", "event_cnt", "event_mask"):
+        assert same_bits(got[key], want[key]), key
+    k = int(r.integers(1, 300))
+    counts = [len(w[0]) for w in wins]
+    out = tef_base.format_windows(packed, (H, W), "cuda", max_num_grad_events=k, generator=torch.Generator().manual_seed(seed))
+    if max(counts) <= k:
+        assert out["d_event_list"].shape[1] == 0 and same_bits(out["event_list"], want["event_list"])
+        return
+    assert out["event_list"].shape[1] == max(min(c, k) for c in counts) and out["d_event_list"].shape[1] == max(max(c - k, 0) for c in counts)
+    for b, n in enumerate(counts):
+        rows = torch.cat([torch.cat([out["event_list"][b], out["event_list_pol_mask"][b]], 1),
+                          torch.cat([out["d_event_list"][b], out["d_event_list_pol_mask"][b]], 1)])
+        rows = rows[rows[:, 4:].abs().sum(1) > 0].cpu().numpy()
+        ref = np.concatenate([want["event_list"][b, :n], want["event_list_pol_mask"][b, :n]], 1)
+        assert rows.shape == ref.shape
+        if n > 1:                                            # one-event windows normalise to NaN timestamps (0/0), like upstream
+            assert np.array_equal(_sorted_cols(rows.T), _sorted_cols(ref.T)), b
