@@ -77,6 +77,11 @@ CASES = [
     ("iterative", 2, 8, 2500, 500, 96, 112, 1, 3, "two", 3.0, True, True, "uniform"),
     ("iterative", 2, 8, 2000, 0, 64, 80, 1, 2, "one", 2.0, False, False, "uniform"),
     ("iterative", 1, 10, 20000, 0, 480, 640, 1, 1, "two", 3.0, False, True, "uniform"),
+    ("iterative", 1, 10, 200000, 0, 480, 640, 1, 1, "two", 3.0, False, True, "uniform"),      # 2 M events: band-major order, many CTAs per segment
+    # heavy pixel reuse (up to 82 events per pixel): the L-inf bound of the gradient is relaxed to 5e-5 -- here the fp32 reference
+    # itself is 0.5 (L-inf) / 0.08 (L2) away from its own fp64 run (events cross pixel boundaries), and summing 80 fp32 terms per
+    # pixel in another order moves isolated gradient pixels by 1.3e-5; the L2 bound stays 1e-5 (measured 2.8e-6)
+    ("iterative", 1, 10, 100000, 20000, 480, 640, 1, 1, "two", 1.0, True, True, "edges", 5e-5),
     ("iterative", 1, 24, 1500, 500, 64, 64, 1, 1, "two", 1.0, False, True, "uniform"),
     ("iterative", 1, 31, 300, 100, 40, 48, 8, 5, "one", 1.0, False, True, "uniform"),       # TEF_MAX_PASSES, TEF_MAX_FLOWS, 5 scales
     ("iterative", 1, 16, 800, 200, 48, 64, 1, 2, "four", 2.0, False, False, "uniform"),
@@ -88,7 +93,8 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-B%d-P%d-N%d+%d-%dx%d-F%d-S%d-%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9]))
 def test_oracle_parity_seeded(case):
-    kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, dist = case
+    kind, B, P, N, Nd, H, W, F, S, mode, sigma, ragged, border, dist = case[:14]
+    grad_linf_tol = case[14] if len(case) > 14 else TOL
     seq = syn.make_sequence(11, B, P, N, Nd, H, W, F, sigma, ragged, dist)
     P_cfg = P // 2 if (mode == "four" and kind == "iterative") else P      # Iterative.__init__ doubles it (loss/flow.py:422-423)
     cfg = syn.loss_config(H, W, B, P_cfg, S, mode)
@@ -101,7 +107,7 @@ def test_oracle_parity_seeded(case):
     assert linf < TOL and l2 < TOL, ("iwe", linf, l2)
     assert np.array_equal(g["iwe"] != 0, o["iwe"] != 0)
     linf, l2 = rel_err(g["gflow"], o["gflow"])
-    assert linf < TOL and l2 < TOL, ("grad", linf, l2)
+    assert linf < grad_linf_tol and l2 < TOL, ("grad", linf, l2)
 
 
 def test_update_contract_and_reset():
