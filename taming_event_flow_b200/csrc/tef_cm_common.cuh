@@ -180,6 +180,7 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
     // bins are laid out by FIXED segment slots (set * P + pass), empty passes included, so that tef_update_pass can count
     // a pass before the later ones are known; the detached set's slots exist only if it has any rows
+    if (2l * d->P * d->B * g.tiles * 128 > 0x7fffffffl) return TEF_ELIMIT;          // bin indices are 32-bit
     const int per_seg = d->B * g.tiles * 128;
     bool any_detached = false;
     for (int s = 0; s < ns; ++s) {
