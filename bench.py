@@ -47,6 +47,10 @@ WORKLOADS = {
     "iterative_480x640_2Mev": dict(B=1, P=10, N=2_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
     "iterative_240x320_1Mev": dict(B=1, P=10, N=1_000_000, Nd=0, H=240, W=320, F=1, S=1, mode="two", sigma=1.5, dist="uniform", warping="Iterative"),
     "iterative_480x640_1Mev_edges": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=3.0, dist="edges", warping="Iterative"),
+    # SURVEY 8d's other input variants: small flow (sigma 0.5 px/window) and ragged batches (per-sample counts U[0.3 N, N], zero-padded)
+    "iterative_480x640_1Mev_sigma05": dict(B=1, P=10, N=1_000_000, Nd=0, H=480, W=640, F=1, S=1, mode="two", sigma=0.5, dist="uniform", warping="Iterative"),
+    "iterative_128x128_b8_f4_ragged": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative",
+                                           ragged=True),
     # BASELINE.json configs[0]: 128x128 crops, batch 8, 10 passes x (10k grad + 10k detached)
     "iterative_128x128_b8_f1": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=1, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
     "iterative_128x128_b8_f4": dict(B=8, P=10, N=10_000, Nd=10_000, H=128, W=128, F=4, S=1, mode="two", sigma=3.0, dist="uniform", warping="Iterative"),
@@ -97,6 +101,9 @@ def fast_sequence(seed, wl, device="cpu", n_override=None):
             ev[:, :, 1] = torch.randint(0, H, (B, n), generator=gen).float()
             ev[:, :, 2] = torch.randint(0, W, (B, n), generator=gen).float()
             ev[:, :, 3] = (torch.randint(0, 2, (B, n), generator=gen) * 2 - 1).float()
+            if wl.get("ragged"):                       # zero rows beyond each sample's own count, like custom_collate
+                counts = (torch.rand(B, generator=gen) * 0.7 + 0.3) * n
+                ev[torch.arange(n)[None, :] >= counts[:, None]] = 0.0
         mk = torch.stack([(ev[:, :, 3] > 0).float(), (ev[:, :, 3] < 0).float()], -1)
         return ev, mk
 
@@ -196,7 +203,7 @@ def workload_config(wl):
         "workload": wl["name"], "warping": wl["warping"], "iterative_mode": wl["mode"], "batch": wl["B"], "passes_loss": wl["P"],
         "events_per_window": wl["N"], "detached_events_per_window": wl["Nd"], "resolution": [wl["H"], wl["W"]],
         "flow_scales": wl["F"], "scales_loss": wl["S"], "event_distribution": wl["dist"], "flow_sigma_px": wl["sigma"],
-        "cache": "inputs_larger_than_L2 (fresh event tensors every step)",
+        "cache": "inputs_larger_than_L2 (fresh event tensors every step)", "ragged": bool(wl.get("ragged", False)),
     }
 
 
@@ -330,6 +337,8 @@ def run_ours(args, wl):
     cfg = syn.loss_config(wl["H"], wl["W"], wl["B"], P, wl["S"], wl["mode"], warping=wl["warping"])
     module = getattr(tef_flow, wl["warping"])(cfg, dev)
     E = events_per_step(wl)
+    if wl.get("ragged"):                               # padding rows are not events
+        E = int(sum((m.sum(-1) > 0).sum().item() for key in ("masks", "d_masks") for m in seq[key]))
     nsteps = args.warmup + args.steps
 
     # ---- device-resident arm: fresh event tensors for every step (update() mutates ts in place)
