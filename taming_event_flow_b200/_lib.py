@@ -149,6 +149,14 @@ def stream():
 
 
 def require_cuda(*tensors):
+    import torch
+
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise TefError("taming_event_flow_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path" % t.device)
+        if t.device.index != torch.cuda.current_device():
+            # the C ABI launches on the current device's stream: a tensor of another GPU would be an illegal address
+            raise TefError("tensor lives on %s but the current CUDA device is cuda:%d; use torch.cuda.set_device / torch.cuda.device"
+                           % (t.device, torch.cuda.current_device()))

@@ -204,7 +204,7 @@ class BaseEventWarping(torch.nn.Module):
         if F > _lib.MAX_FLOWS:
             raise _lib.TefError("at most %d flow maps per pass" % _lib.MAX_FLOWS)
         f0 = flow_list[0]
-        if not f0.is_cuda:
+        if not f0.is_cuda or f0.device.index != torch.cuda.current_device():
             require_cuda(f0)
         B, C, H, W = f0.shape
         if C != 2 or H != self.res[0] or W != self.res[1]:

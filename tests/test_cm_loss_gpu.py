@@ -329,3 +329,23 @@ def test_fused_histogram_equals_forward_histogram_and_forward_twice(kind, monkey
         out[fused] = (first, loss.item(), torch.stack([f.grad for per in flows for f in per]).cpu())
     assert out[True][0] == out[True][1] == out[False][0] == out[False][1]
     assert torch.equal(out[True][2], out[False][2])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_of_another_device_are_rejected():
+    """The C ABI launches on the current device: tensors of another GPU must fail loudly, not fault."""
+    from taming_event_flow_b200._lib import TefError
+    from taming_event_flow_b200.dataloader.encodings import events_to_channels
+    from taming_event_flow_b200.loss.flow import Iterative
+
+    torch.cuda.set_device(0)
+    other = torch.device("cuda", 1)
+    with pytest.raises(TefError):
+        events_to_channels(torch.zeros(4, device=other), torch.zeros(4, device=other), torch.ones(4, device=other), (8, 8))
+    m = Iterative(syn.loss_config(16, 16, 1, 2, 1, "two"), other)
+    with pytest.raises(TefError):
+        m.update([torch.zeros(1, 2, 16, 16, device=other)], torch.zeros(1, 4, 4, device=other), torch.zeros(1, 4, 2, device=other),
+                 torch.zeros(1, 0, 4, device=other), torch.zeros(1, 0, 2, device=other))
+    with torch.cuda.device(other):                           # and it works once the device is current
+        m.update([torch.zeros(1, 2, 16, 16, device=other)], torch.zeros(1, 4, 4, device=other), torch.ones(1, 4, 2, device=other),
+                 torch.zeros(1, 0, 4, device=other), torch.zeros(1, 0, 2, device=other))
