@@ -78,7 +78,7 @@ struct CmParams {
     float2 *gflow;
     float2 *img;             // deterministic mode: same layout with every float replaced by an int64 (twice the bytes)
     float2 *gimg;            // deterministic mode: gradient images [F][B][slot][phase][pol][H][Wp] float2 (otherwise in place in img)
-    float2 *posbuf;          // [(P+1)][rows_grad] chain positions of the gradient-carrying rows (Iterative)
+    float2 *posbuf;          // [(P+1)][rows_grad] chain positions (x, y) of the gradient-carrying rows (Iterative)
     uint32_t *alivebuf;      // [F][rows_grad] cumulative in-image bits (bit tref)
     long rows_grad;
     double *acc_sum;
@@ -318,6 +318,36 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
                 }
             }
         }
+    }
+}
+
+// splat<true, false> for a one-hot {0,1} polarity mask -- the only kind the reference's loader produces
+// (dataloader/base.py:264-278) -- on packed fp32x2 arithmetic, for a position (x, y) that satisfies inside().
+// Same values and the same set of reductions as splat():
+//  * the in-image tests of the bottom / right corners are implied by the weights: floor(v + 1) > size - 1 needs
+//    v + 1 >= size, i.e. |v - corner| >= 1, whose clamped weight is an exact 0;
+//  * v - floor(v) is exact and < 1, so the top / left weights are >= 2^-24: the top row always has a non-zero weight
+//    (never skipped), and the bottom row has two zero weights exactly when its row weight is 0 (products of weights
+//    >= 2^-24 do not underflow);
+//  * a bottom row that is not skipped has floor(y + 1) == floor(y) + 1.
+// `pol_plane` = slot base + polarity * plane.
+__device__ __forceinline__ void splat_inside_1hot(float2 *__restrict__ pol_plane, const ImgGeom &g, float2 p /* (x, y) */, float nts) {
+    const float2 c0 = make_float2(floorf(p.x), floorf(p.y));
+    const float2 p1 = add2(p, bc(1.0f));
+    const float2 c1 = make_float2(floorf(p1.x), floorf(p1.y));
+    const float2 d0 = sub2(p, c0), d1_ = sub2(p, c1);
+    const float2 u0 = sub2(bc(1.0f), make_float2(fabsf(d0.x), fabsf(d0.y)));      // utils/iwe.py:96-99
+    const float2 u1 = sub2(bc(1.0f), make_float2(fabsf(d1_.x), fabsf(d1_.y)));
+    const float2 wx = make_float2(fmaxf(0.0f, u0.x), fmaxf(0.0f, u1.x));          // (left, right)
+    const float wy0 = fmaxf(0.0f, u0.y), wy1 = fmaxf(0.0f, u1.y);
+    const int xl = (int)c0.x, phase = xl & 1;
+    const unsigned off = (unsigned)(phase * 2 * (int)g.plane + (int)c0.y * g.Wp + xl + phase);      // a slot is far below 2^31 elements
+    char *base = reinterpret_cast<char *>(pol_plane);
+    const float2 a = mul2(bc(wy0), wx);                                            // (w_left, w_right) of the top row
+    red_add_v4(reinterpret_cast<float2 *>(base + (size_t)off * 8u), a.x, a.x * nts, a.y, a.y * nts);
+    if (wy1 != 0.0f) {
+        const float2 b = mul2(bc(wy1), wx);
+        red_add_v4(reinterpret_cast<float2 *>(base + (size_t)(off + (unsigned)g.Wp) * 8u), b.x, b.x * nts, b.y, b.y * nts);
     }
 }
 

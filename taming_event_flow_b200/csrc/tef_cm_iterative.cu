@@ -39,49 +39,54 @@ namespace tef {
 // loops rolled and the register count low for any P; they never travel to HBM.
 // The pass index t is uniform per CTA, so the loop bounds do not diverge.
 // ---------------------------------------------------------------------------------
+// One chain step from position q = (x, y): sample the map, move by dt * flow (utils/iwe.py:14).  The move stays scalar:
+// ptxas contracts a packed product feeding a packed sum into FFMA2 (see tef_device.cuh), the reference rounds twice.
+__device__ __forceinline__ float2 chain_step(const float2 *__restrict__ map, const Res &r, float2 q, float dt, bool safe) {
+    float2 v;                                          // (x-flow, y-flow)
+    if (safe) v = sample_flow_inside_xy<false>(map, r, q, nullptr);
+    else v = sample_flow<false>(map, r, q.y, q.x, nullptr);
+    return make_float2(q.x + dt * v.x, q.y + dt * v.y);
+}
 __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
-                                               int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads] */,
+                                               int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads], (x, y) */,
                                                float2 *__restrict__ pb /* this row of posbuf (stride rows_grad) or nullptr */,
                                                int keep_lo, int keep_hi /* nodes some scale splats for this pass; the others only feed the mask */) {
     const long stride = (long)p.B * 2 * p.res.fplane;   // one pass further (dual-phase maps)
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
     const bool in0 = inside(y0, x0, p.res);
-    float y = y0, x = x0, tprev = ts;
+    float2 q = make_float2(x0, y0);
+    float tprev = ts;
     bool al = true, safe = in0;
     const float2 *map = flow_fb + (long)t * stride;
     float2 *pw = pos + (t + 1) * kThreads + threadIdx.x;
     for (int tr = t + 1; tr <= p.P; ++tr, map += stride, pw += kThreads) {   // forward: sample map tr-1, land on node tr
         if (al) {
-            const float2 v = safe ? sample_flow_inside<false>(map, p.res, y, x, nullptr) : sample_flow<false>(map, p.res, y, x, nullptr);
-            const float dt = (float)tr - tprev;    // utils/iwe.py:14
-            y = y + dt * v.y; x = x + dt * v.x;
-            al = inside(y, x, p.res);              // utils/iwe.py:52-59
+            q = chain_step(map, p.res, q, (float)tr - tprev, safe);
+            al = inside(q.y, q.x, p.res);              // utils/iwe.py:52-59
             if (al) alive |= (1u << tr);
             safe = true;
         }
         tprev = (float)tr;
         if (tr <= keep_hi) {
-            *pw = make_float2(y, x);
-            if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));   // coalesced streaming store (evict-first), kept for the backward kernel
+            *pw = q;
+            if (pb) __stcs(pb + (long)tr * p.rows_grad, q);   // coalesced streaming store (evict-first), kept for the backward kernel
         }
     }
-    y = y0; x = x0; tprev = ts; al = true; safe = in0;
+    q = make_float2(x0, y0); tprev = ts; al = true; safe = in0;
     map = flow_fb + (long)t * stride;
     pw = pos + t * kThreads + threadIdx.x;
     for (int tr = t; tr >= 0; --tr, map -= stride, pw -= kThreads) {         // backward: sample map tr, land on node tr
         if (al) {
-            const float2 v = safe ? sample_flow_inside<false>(map, p.res, y, x, nullptr) : sample_flow<false>(map, p.res, y, x, nullptr);
-            const float dt = (float)tr - tprev;
-            y = y + dt * v.y; x = x + dt * v.x;
-            al = inside(y, x, p.res);
+            q = chain_step(map, p.res, q, (float)tr - tprev, safe);
+            al = inside(q.y, q.x, p.res);
             if (al) alive |= (1u << tr);
             safe = true;
         }
         tprev = (float)tr;
         if (tr >= keep_lo) {
-            *pw = make_float2(y, x);
-            if (pb) __stcs(pb + (long)tr * p.rows_grad, make_float2(y, x));
+            *pw = q;
+            if (pb) __stcs(pb + (long)tr * p.rows_grad, q);
         }
     }
     return alive;
@@ -145,6 +150,21 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
     if (!has) return;
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;          // float2 elements per slot (int64 pairs in deterministic mode)
     float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
+    if (!DET && p.border && ((m.x == 1.0f && m.y == 0.0f) || (m.x == 0.0f && m.y == 1.0f))) {
+        // the loader's masks: one polarity plane, weights not scaled, every splatted node inside the image
+        float2 *img_pol = img_fb + (m.x != 0.0f ? 0 : p.ig.plane);
+        for (int s = 0; s < p.sc.S; ++s) {
+            if (!((has >> s) & 1u)) continue;
+            const WinS w = sw[s];
+            float2 *slot = img_pol + (long)(w.slot0 + w.tr0) * slot_stride;
+            const float2 *pq = pos + w.tr0 * kThreads + threadIdx.x;
+            for (int tr = w.tr0; tr <= w.tr1; ++tr, slot += slot_stride, pq += kThreads) {
+                const float nts = 1.0f - div_const(fabsf((float)tr - e.x), w.fdelta, w.rdelta);   // loss/flow.py:94-95
+                splat_inside_1hot(slot, p.ig, *pq, nts);
+            }
+        }
+        return;
+    }
     for (int s = 0; s < p.sc.S; ++s) {
         if (!((has >> s) & 1u)) continue;
         const WinS w = sw[s];
@@ -152,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
             if (!p.border && !((alive >> tr) & 1u)) continue;
             const float nts = 1.0f - div_const(fabsf((float)tr - e.x), w.fdelta, w.rdelta);   // loss/flow.py:94-95
             const float2 q = pos[tr * kThreads + threadIdx.x];
-            splat<true, DET>(img_fb + (long)(w.slot0 + tr) * slot_stride, p.res, p.ig, q.x, q.y, nts, m);
+            splat<true, DET>(img_fb + (long)(w.slot0 + tr) * slot_stride, p.res, p.ig, q.y, q.x, nts, m);
         }
     }
 }
@@ -209,12 +229,12 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         if (tr >= w0_tr0 && tr <= w0_tr1) {
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), w0_fdelta, w0_rdelta);
-            iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+            iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.y, q.x, nts, m, gy, gx);
         }
         for (int s = 1; s < p.sc.S; ++s) {
             if (!((has >> s) & 1u) || tr < sw[s].tr0 || tr > sw[s].tr1) continue;
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), sw[s].fdelta, sw[s].rdelta);
-            iwe_grad<true>(img_fb + (long)(sw[s].slot0 + tr) * gslot, p.res, p.ig, q.x, q.y, nts, m, gy, gx);
+            iwe_grad<true>(img_fb + (long)(sw[s].slot0 + tr) * gslot, p.res, p.ig, q.y, q.x, nts, m, gy, gx);
         }
     };
 
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         float2 q = (tr >= t + 1) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr >= t + 1; --tr, pq -= p.rows_grad, map -= map_stride, gmap -= gmap_stride) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(y0, x0) : __ldcs(pq - p.rows_grad);
+            const float2 src = first ? make_float2(x0, y0) : __ldcs(pq - p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : 1.0f;
-                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }
@@ -252,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         float2 q = (tr <= t) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr <= t; ++tr, pq += p.rows_grad, map += map_stride, gmap += gmap_stride) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(y0, x0) : __ldcs(pq + p.rows_grad);
+            const float2 src = first ? make_float2(x0, y0) : __ldcs(pq + p.rows_grad);
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             if (gpy != 0.f || gpx != 0.f) {
                 const float dt = first ? ((float)tr - ts) : -1.0f;
-                step_bwd<DET>(map, gmap, p.res, p.ig, src.x, src.y, dt, gpy, gpx, cy_, cx_);
+                step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
             }
             q = src;
         }

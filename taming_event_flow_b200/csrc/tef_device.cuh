@@ -19,12 +19,44 @@ struct Res {
     float sh, sw;     // (H-1)/2, (W-1)/2  (ATen's align_corners=True scaling factor)
     float rhm1, rwm1; // RN(1/hm1), RN(1/wm1) for div_const()
     int Wp, fplane;   // packed flow maps: padded row length (even, >= W+2) and plane size (H+1)*Wp, see sample_flow()
+    float2 m1_xy, rm1_xy, s_xy;   // the same constants as (x, y) pairs for the packed fp32x2 path: (wm1, hm1), (rwm1, rhm1), (sw, sh)
     __host__ __device__ static Res make(int H, int W) {
         Res r; r.H = H; r.W = W; r.hm1 = (float)(H - 1); r.wm1 = (float)(W - 1);
         r.sh = r.hm1 / 2.0f; r.sw = r.wm1 / 2.0f; r.rhm1 = 1.0f / r.hm1; r.rwm1 = 1.0f / r.wm1;
-        r.Wp = (W + 3) & ~1; r.fplane = (H + 1) * r.Wp; return r;
+        r.Wp = (W + 3) & ~1; r.fplane = (H + 1) * r.Wp;
+        r.m1_xy.x = r.wm1; r.m1_xy.y = r.hm1; r.rm1_xy.x = r.rwm1; r.rm1_xy.y = r.rhm1; r.s_xy.x = r.sw; r.s_xy.y = r.sh;
+        return r;
     }
 };
+
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 of sm_100a): two independent IEEE round-to-nearest fp32 operations
+// per issue slot, each half rounded exactly like the scalar instruction (no FTZ), so results stay bit-identical to the
+// scalar code.  The event kernels are bound by instruction issue, and their per-event arithmetic
+// comes in (x, y) pairs.  ptxas folds negation, |.| and scalar broadcast (`bc`) into the operands.
+// CAUTION: unlike the scalar mul.rn / add.rn, ptxas (12.9) CONTRACTS a mul2 whose only use is an add2 into one FFMA2,
+// even with --fmad=false.  Never feed a mul2 result into an add2 / sub2: keep such a step scalar.  tests/test_cabi.py
+// counts the FFMA2 instructions of the event kernels against the explicit fma2() calls.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return add2(a, neg2(b)); }    // a - b == a + (-b) in IEEE arithmetic
 
 // IEEE-correct a / c for a divisor known in advance, rc = RN(1/c): one Newton correction of the product
 // (Markstein).  Three instructions instead of the generic division's rcp + refinement + range check.
@@ -113,36 +145,54 @@ __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, co
 // Same sample for a position known to satisfy inside(): then 0 <= iy <= H-1 and 0 <= ix <= W-1 exactly
 // (gy + 1 is in [0, 2]), so both tap rows exist and no bounds test is needed at all (zero padding).
 // Bit-identical to sample_flow() on such positions.
+// The arithmetic is packed fp32x2 on (x, y) pairs: 19 floating-point issue slots instead of 32.
+// div_const()'s guard becomes: exact division only for a non-zero numerator below 1e-30; a zero numerator may take
+// the corrected product, which returns +0 where a / c returns the numerator's signed zero -- the "- 1.0f" that
+// follows gives -1 either way.
 template <bool KEEP>
-__device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
-    const float gy = div_const(2.0f * y, r.hm1, r.rhm1) - 1.0f;
-    const float gx = div_const(2.0f * x, r.wm1, r.rwm1) - 1.0f;
-    const float iy = (gy + 1.0f) * r.sh, ix = (gx + 1.0f) * r.sw;
-    const float fy0 = floorf(iy), fx0 = floorf(ix);
-    const float w_ = ix - fx0, e_ = 1.0f - w_;
-    const float n_ = iy - fy0, s_ = 1.0f - n_;
-    const int y0 = (int)fy0, x0 = (int)fx0;
-    const float4 *p = tap_row(map, r, y0, x0);
+__device__ __forceinline__ float2 sample_flow_inside_xy(const float2 *__restrict__ map, const Res &r, float2 p /* (x, y) */, Taps *tp) {
+    const float2 a = add2(p, p);                                   // 2.0f * v (exact either way)
+    float2 g;
+    if ((fabsf(a.x) >= 1e-30f || a.x == 0.0f) && (fabsf(a.y) >= 1e-30f || a.y == 0.0f)) {
+        const float2 q0 = mul2(a, r.rm1_xy);
+        const float2 r0 = fma2(neg2(q0), r.m1_xy, a);
+        g = fma2(r0, r.rm1_xy, q0);
+    } else {
+        g = make_float2(a.x / r.wm1, a.y / r.hm1);
+    }
+    g = add2(g, bc(-1.0f));                                        // utils/iwe.py:30-31
+    const float2 i = mul2(add2(g, bc(1.0f)), r.s_xy);              // ATen unnormalize: (ix, iy)
+    const float2 fl = make_float2(floorf(i.x), floorf(i.y));
+    const float2 fr = sub2(i, fl);                                 // (w_, n_)
+    const float2 om = sub2(bc(1.0f), fr);                          // (e_, s_)
+    const int x0 = (int)fl.x, y0 = (int)fl.y;
+    const float4 *q = tap_row(map, r, y0, x0);
 #ifdef TEF_EXP_NO_GATHER
     const float4 top = make_float4(0.3f * (float)(x0 & 7), -0.2f, 0.1f, 0.4f), bot = make_float4(0.2f, 0.1f * (float)(y0 & 3), -0.3f, 0.2f);
-    if (p == nullptr) return make_float2(0.f, 0.f);
+    if (q == nullptr) return make_float2(0.f, 0.f);
 #else
-    const float4 top = __ldg(p), bot = __ldg(p + (r.Wp >> 1));
+    const float4 top = __ldg(q), bot = __ldg(q + (r.Wp >> 1));
 #endif
-    const float w0 = s_ * e_, w1 = s_ * w_, w2 = n_ * e_, w3 = n_ * w_;
-    float ox = top.x * w0, oy = top.y * w0;
-    ox = __fmaf_rn(top.z, w1, ox); oy = __fmaf_rn(top.w, w1, oy);
-    ox = __fmaf_rn(bot.x, w2, ox); oy = __fmaf_rn(bot.y, w2, oy);
-    ox = __fmaf_rn(bot.z, w3, ox); oy = __fmaf_rn(bot.w, w3, oy);
+    const float2 ew = make_float2(om.x, fr.x);                     // (e_, w_)
+    const float2 w01 = mul2(bc(om.y), ew);                         // s_*e_, s_*w_
+    const float2 w23 = mul2(bc(fr.y), ew);                         // n_*e_, n_*w_
+    float2 o = mul2(make_float2(top.x, top.y), bc(w01.x));         // (x-flow, y-flow): nw*w0, then three FMAs like ATen
+    o = fma2(make_float2(top.z, top.w), bc(w01.y), o);
+    o = fma2(make_float2(bot.x, bot.y), bc(w23.x), o);
+    o = fma2(make_float2(bot.z, bot.w), bc(w23.y), o);
     if (KEEP) {
         const bool oy1 = y0 + 1 < r.H, ox1 = x0 + 1 < r.W;
-        tp->w[0] = w0; tp->w[1] = w1; tp->w[2] = w2; tp->w[3] = w3;
+        tp->w[0] = w01.x; tp->w[1] = w01.y; tp->w[2] = w23.x; tp->w[3] = w23.y;
         tp->v[0] = make_float2(top.x, top.y); tp->v[1] = make_float2(top.z, top.w);
         tp->v[2] = make_float2(bot.x, bot.y); tp->v[3] = make_float2(bot.z, bot.w);
         tp->ok[0] = true; tp->ok[1] = ox1; tp->ok[2] = oy1; tp->ok[3] = oy1 && ox1;
-        tp->ax = w_; tp->ay = n_; tp->y0 = y0; tp->x0 = x0;
+        tp->ax = fr.x; tp->ay = fr.y; tp->y0 = y0; tp->x0 = x0;
     }
-    return make_float2(ox, oy);
+    return o;
+}
+template <bool KEEP>
+__device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
+    return sample_flow_inside_xy<KEEP>(map, r, make_float2(x, y), tp);
 }
 
 // get_event_flow (utils/iwe.py:17-40) of one location (y, x) on planar maps [H][W]: ATen's bilinear grid_sample

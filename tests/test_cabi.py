@@ -76,3 +76,32 @@ def test_product_code_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dp, f)).read()
                 assert not pat.search(src), os.path.join(dp, f)
+
+
+def test_no_contracted_packed_multiply_adds_in_the_event_kernels():
+    """ptxas 12.9 contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one FFMA2 even with --fmad=false, which would
+    break the bit-faithful per-event arithmetic (csrc/tef_device.cuh).  The only FFMA2 the event kernels may contain are
+    the explicit fma2() calls of sample_flow_inside_xy: 2 (division by a constant) + 3 (tap accumulation, dead in the
+    backward kernel, which only needs the taps) per inlined copy, two copies per kernel."""
+    import shutil
+    import subprocess
+
+    import pytest
+
+    from taming_event_flow_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.build()
+    expect = {"iter_fwd_kernelILb0E": 10, "iter_fwd_kernelILb1E": 10, "iter_bwd_kernelILb0E": 4, "iter_bwd_kernelILb1E": 4}
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    counts, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = next((k for k in expect if k in m.group(1)), None)
+        elif cur and "FFMA2" in line:
+            counts[cur] = counts.get(cur, 0) + 1
+    assert counts == expect, counts
+

@@ -349,3 +349,35 @@ def test_tensors_of_another_device_are_rejected():
     with torch.cuda.device(other):                           # and it works once the device is current
         m.update([torch.zeros(1, 2, 16, 16, device=other)], torch.zeros(1, 4, 4, device=other), torch.ones(1, 4, 2, device=other),
                  torch.zeros(1, 0, 4, device=other), torch.zeros(1, 0, 2, device=other))
+
+
+def test_sparse_events_images_are_bit_identical_to_the_oracle():
+    """Events so far apart that every image pixel receives at most one non-zero contribution: the fp32 summation order
+    no longer matters, so the slot images must equal the oracle's BIT FOR BIT.  This pins the per-event arithmetic of
+    the fused forward kernel -- the packed fp32x2 chain step and the one-hot splat -- to the reference's rounding
+    (a contracted multiply-add, which ptxas 12.9 introduces for packed mul -> add pairs, would move the weights)."""
+    B, P, H, W, F = 1, 4, 128, 128, 2
+    gen = torch.Generator().manual_seed(5)
+    flows, events, masks, d_events, d_masks = [], [], [], [], []
+    for t in range(P):
+        flows.append([syn.make_flow(gen, B, H, W, 0.3).clamp_(-0.4, 0.4) for _ in range(F)])
+        for k, (evs, mks) in enumerate(((events, masks), (d_events, d_masks))):
+            # window t at columns 32 i + 8 t, set k at rows 32 j + 16 k: total displacement <= 4 x 0.4 px, splats never overlap
+            ii, jj = torch.meshgrid(torch.arange(4), torch.arange(4), indexing="ij")
+            x = (32 * ii + 8 * t).reshape(-1).float()
+            y = (32 * jj + 16 * k).reshape(-1).float()
+            n = x.numel()
+            ts, _ = torch.sort(torch.rand(n, generator=gen))
+            pol = (torch.randint(0, 2, (n,), generator=gen) * 2 - 1).float()
+            ev = torch.stack([ts, y, x, pol], -1)[None].contiguous()
+            evs.append(ev)
+            mks.append(torch.stack([(pol > 0).float(), (pol < 0).float()], -1)[None].contiguous())
+    cfg = syn.loss_config(H, W, B, P, 1, "two")
+    g = _run_gpu("iterative", cfg, flows, events, masks, d_events, d_masks, backward=False)
+    o = orc.iterative(orc.make_cfg(B, H, W, P, F, 1, "two", True), flows, events, masks, d_events, d_masks, np.float32, want_grad=False, want_iwe=True)
+    assert (o["iwe"] != 0).sum() > 4 * 2 * 16 * P                     # the case is not degenerate
+    # no pixel of any count image holds more than one event (weights sum to <= 1 per event)
+    assert o["iwe"][:, :, :, 0:2].max() <= 1.0
+    assert np.array_equal(g["iwe"], o["iwe"])
+    assert g["loss"] == pytest.approx(float(o["loss"]), rel=1e-6)
+
