@@ -16,7 +16,19 @@ __global__ void __launch_bounds__(kThreads) mb_red_kernel(float4 *buf, uint32_t 
     const uint32_t warp_base = ((blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 40503u * 256u) & (slots - 1);
     for (int i = 0; i < iters; ++i) {
         const uint32_t r = lcg(s) >> 8;
-        const uint32_t a = mode == 0 ? (r & (slots - 1)) : ((warp_base + (r & 255u) + (uint32_t)i * 64u) & (slots - 1));
+        uint32_t a = mode == 0 ? (r & (slots - 1)) : ((warp_base + (r & 255u) + (uint32_t)i * 64u) & (slots - 1));
+        // access-pattern probes (scripts/red_patterns.py): 2 = 32 consecutive 16-byte slots per warp, 3 = one slot for the whole warp,
+        // 4 = lane pairs share a slot, 5 = lane pairs share a 32-byte sector (different halves), 6 = lane quads share a slot
+        const uint32_t lane = threadIdx.x & 31u;
+        if (mode == 2) a = (warp_base + lane + (uint32_t)i * 32u) & (slots - 1);
+        else if (mode == 3) a = (warp_base + (uint32_t)i) & (slots - 1);
+        else if (mode >= 4) {
+            const uint32_t g = mode == 6 ? (lane >> 2) : (lane >> 1);
+            uint32_t h = (warp_base * 31u + g * 2654435761u + (uint32_t)i * 40503u);      // same value for the lanes of a group
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            const uint32_t slot = (warp_base + (h & 255u) + (uint32_t)i * 64u) & (slots - 1);
+            a = mode == 5 ? ((slot & ~1u) | (lane & 1u)) : slot;
+        }
         red_add_v4(reinterpret_cast<float2 *>(buf + a), 1.0f, 0.5f, 0.25f, 0.125f);
     }
 }
