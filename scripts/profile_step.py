@@ -1,7 +1,7 @@
 """Run a few plain steps of one bench.py workload (update x P -> forward -> backward) for ncu / compute-sanitizer.
 
-    ncu --set full --clock-control none --import-source on -k regex:iter_ -s 2 -c 2 -o gpurun_out/prof \\
-        python scripts/profile_step.py --workload iterative_480x640_1Mev --steps 2
+    ncu --set full --clock-control none --import-source on -k regex:iter_ -s 6 -c 2 -o gpurun_out/prof \\
+        python scripts/profile_step.py --workload iterative_480x640_1Mev --steps 5
 """
 import argparse
 import os
