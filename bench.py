@@ -211,7 +211,7 @@ def workload_config(wl):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML in a thread, every 20 ms).
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in a thread, every 4 ms).
     Started before the warm-up so that NVML initialisation does not land inside the timed region."""
 
     def __init__(self, index):
@@ -235,7 +235,7 @@ class ClockSampler:
                 self.rows.append((sm, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def start(self):
         if self.nv is None:
