@@ -68,7 +68,7 @@ typedef struct tef_cm_desc {
     void *sort_bins;       /* int [nbins + 1]  tile-sort histogram / offsets           */
     void *sort_sums;       /* int scan scratch                                         */
     void *sorted_ev;       /* 32-byte records [rows]: (ts, y, x, sample index bits, mask+, mask-, 0, 0), tile-sorted */
-    void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (Iterative)   */
+    void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (x, y) (Iterative) */
     void *alivebuf;        /* uint32 [F][rows_grad] cumulative in-image bits (bit tref) */
     void *gimg;            /* deterministic mode only: gradient images float2 [F][B][slots][phase][pol][H][Wp] */
     int hist_done;         /* 1: every tef_update_pass of this window already counted its events into sort_bins (fused histogram),
