@@ -14,7 +14,8 @@ L = _lib.lib()
 buf = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")
 st = _lib.stream()
 names = {0: "random over 64 MB", 1: "random in a 4 KB window per warp", 2: "32 consecutive slots per warp (512 B)", 3: "one slot for the whole warp",
-         4: "lane pairs share a slot", 5: "lane pairs share a 32-byte sector", 6: "lane quads share a slot"}
+         4: "lane pairs share a slot", 5: "lane pairs share a 32-byte sector", 6: "lane quads share a slot",
+         7: "pairs share a slot, merged in software", 8: "random in 4 KB, merge attempted (cost)"}
 for mode, name in names.items():
     ops = ctypes.c_long()
     best = 1e30

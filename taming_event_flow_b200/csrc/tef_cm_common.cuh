@@ -181,6 +181,7 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     // bins are laid out by FIXED segment slots (set * P + pass), empty passes included, so that tef_update_pass can count
     // a pass before the later ones are known; the detached set's slots exist only if it has any rows
     if (2l * d->P * d->B * g.tiles * 128 > 0x7fffffffl) return TEF_ELIMIT;          // bin indices are 32-bit
+    if ((long)d->B * 4 * p.ig.plane > 0x7fffffffl) return TEF_ELIMIT;               // merge keys (sample * slot size + offset) are 31-bit
     const int per_seg = d->B * g.tiles * 128;
     bool any_detached = false;
     for (int s = 0; s < ns; ++s) {
@@ -348,6 +349,57 @@ __device__ __forceinline__ void splat_inside_1hot(float2 *__restrict__ pol_plane
     if (wy1 != 0.0f) {
         const float2 b = mul2(bc(wy1), wx);
         red_add_v4(reinterpret_cast<float2 *>(base + (size_t)(off + (unsigned)g.Wp) * 8u), b.x, b.x * nts, b.y, b.y * nts);
+    }
+}
+
+// Warp-level merge of equal reduction addresses (DESIGN.md decision 13: the reduction path charges one sector per lane
+// whatever the addresses, and tile-sorted events put equal addresses on neighbouring lanes).  `key` identifies the 16-byte
+// slot a lane is about to reduce into (lanes without work pass a key no other lane has).  One round: inside every run of
+// equal keys the lanes of odd rank hand their values to the lane before them.  Returns true for a lane that gave its
+// values away; the receivers' v[] hold the sums.  Must be called by all 32 lanes.
+template <int NV>
+__device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned lane, float (&v)[NV]) {
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool same = lane > 0u && key == prev;
+    const unsigned heads = __ballot_sync(0xffffffffu, !same);               // first lane of every run
+    if (heads == 0xffffffffu) return false;                                // nothing to merge in this warp (uniform branch)
+    const unsigned start = 31u - (unsigned)__clz(heads & (0xffffffffu >> (31u - lane)));
+    const bool give = ((lane - start) & 1u) != 0u;
+    const unsigned givers = __ballot_sync(0xffffffffu, give);
+    const bool recv = lane < 31u && ((givers >> (lane + 1u)) & 1u) != 0u;   // the next lane is in my run and has odd rank
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float n = __shfl_down_sync(0xffffffffu, v[k], 1);
+        if (recv) v[k] += n;
+    }
+    return give;
+}
+
+// splat_inside_1hot for a whole warp, with equal slots of neighbouring lanes merged before they leave the SM.  `on` = this
+// lane has an event to splat (the others only take part in the shuffles); `plane_sel` = polarity (0 / 1).  Both image rows
+// of a splat share one key (equal top slots imply equal bottom slots); a lane whose own bottom row has weight 0 carries
+// zeros there, and the bottom row is reduced when the merged row weight is non-zero (then the row exists: the
+// contributor that supplied it shares the cell).  Lanes of one warp may belong to different samples (same slot offsets,
+// different images), hence `key_base`.  Must be called by all 32 lanes.
+__device__ __forceinline__ void splat_inside_1hot_warp(float2 *__restrict__ slot_base, const ImgGeom &g, float2 p /* (x, y) */, float nts,
+                                                       int plane_sel, bool on, unsigned lane, unsigned key_base /* sample * slot size */) {
+    const float2 c0 = make_float2(floorf(p.x), floorf(p.y));
+    const float2 p1 = add2(p, bc(1.0f));
+    const float2 c1 = make_float2(floorf(p1.x), floorf(p1.y));
+    const float2 d0 = sub2(p, c0), d1_ = sub2(p, c1);
+    const float2 u0 = sub2(bc(1.0f), make_float2(fabsf(d0.x), fabsf(d0.y)));      // utils/iwe.py:96-99
+    const float2 u1 = sub2(bc(1.0f), make_float2(fabsf(d1_.x), fabsf(d1_.y)));
+    const float2 wx = make_float2(fmaxf(0.0f, u0.x), fmaxf(0.0f, u1.x));          // (left, right)
+    const float wy0 = fmaxf(0.0f, u0.y), wy1 = fmaxf(0.0f, u1.y);
+    const int xl = (int)c0.x, phase = xl & 1;
+    const unsigned off = (unsigned)((phase * 2 + plane_sel) * (int)g.plane + (int)c0.y * g.Wp + xl + phase);   // a slot is far below 2^31 elements
+    const float2 a = mul2(bc(wy0), wx), b = mul2(bc(wy1), wx);                    // (w_left, w_right) of the top / bottom row
+    float v[8] = { a.x, a.x * nts, a.y, a.y * nts, b.x, b.x * nts, b.y, b.y * nts };
+    const bool gave = merge_equal_neighbours<8>(on ? key_base + off : (0x80000000u | lane), lane, v);   // real keys stay below 2^31 (fill_params)
+    if (on && !gave) {
+        char *base = reinterpret_cast<char *>(slot_base);
+        red_add_v4(reinterpret_cast<float2 *>(base + (size_t)off * 8u), v[0], v[1], v[2], v[3]);
+        if (v[4] != 0.0f) red_add_v4(reinterpret_cast<float2 *>(base + (size_t)(off + (unsigned)g.Wp) * 8u), v[4], v[5], v[6], v[7]);
     }
 }
 

@@ -134,37 +134,44 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
     int t, b, row, set; float4 e; float2 m;
     const bool live = locate_sorted(p, t, b, e, m, row, set);
     build_windows(p, t, sw);
-    if (!live) return;
     const int f = blockIdx.y;
-
-    // gradient-carrying rows keep their chain for the backward kernel
-    float2 *pb = (set == 0 && p.posbuf) ? p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row : nullptr;
-    // nodes that any scale splats for this pass (uniform per CTA): only those are kept, on chip and for the backward kernel
-    int keep_lo = p.P + 1, keep_hi = -1;
-    for (int s = 0; s < p.sc.S; ++s)
-        if (sw[s].valid) { keep_lo = min(keep_lo, sw[s].tr0); keep_hi = max(keep_hi, sw[s].tr1); }
-    const uint32_t alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb, keep_lo, keep_hi);
-    if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
-
-    const uint32_t has = active_scales(p, sw, alive);
-    if (!has) return;
     const long slot_stride = (DET ? 8 : 4) * p.ig.plane;          // float2 elements per slot (int64 pairs in deterministic mode)
-    float2 *img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
-    if (!DET && p.border && ((m.x == 1.0f && m.y == 0.0f) || (m.x == 0.0f && m.y == 1.0f))) {
-        // the loader's masks: one polarity plane, weights not scaled, every splatted node inside the image
-        float2 *img_pol = img_fb + (m.x != 0.0f ? 0 : p.ig.plane);
+    float2 *img_fb = nullptr;
+    uint32_t alive = 0, has = 0;
+    if (live) {                                                   // threads without an event stay for the warp-level merge below
+        // gradient-carrying rows keep their chain for the backward kernel
+        float2 *pb = (set == 0 && p.posbuf) ? p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row : nullptr;
+        // nodes that any scale splats for this pass (uniform per CTA): only those are kept, on chip and for the backward kernel
+        int keep_lo = p.P + 1, keep_hi = -1;
+        for (int s = 0; s < p.sc.S; ++s)
+            if (sw[s].valid) { keep_lo = min(keep_lo, sw[s].tr0); keep_hi = max(keep_hi, sw[s].tr1); }
+        alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb, keep_lo, keep_hi);
+        if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
+        has = active_scales(p, sw, alive);
+        img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
+    }
+    // The loader's masks are one-hot {0,1}: one polarity plane, weights not scaled, every splatted node inside the image.
+    // If that holds for every event of the warp, the warp splats together and merges equal slots of neighbouring lanes.
+    const bool fast = !DET && p.border && (!has || (m.x == 1.0f && m.y == 0.0f) || (m.x == 0.0f && m.y == 1.0f));
+    if (__all_sync(0xffffffffu, fast)) {
+        const unsigned lane = threadIdx.x & 31u;
+        const int pol = (has && m.x == 0.0f) ? 1 : 0;
+        const float ts = has ? e.x : 0.0f;
+        const unsigned key_base = has ? (unsigned)b * (unsigned)(4 * p.ig.plane) : 0u;
         for (int s = 0; s < p.sc.S; ++s) {
-            if (!((has >> s) & 1u)) continue;
             const WinS w = sw[s];
-            float2 *slot = img_pol + (long)(w.slot0 + w.tr0) * slot_stride;
+            if (!w.valid) continue;                               // uniform per CTA, like the range of reference times
+            const bool on = ((has >> s) & 1u) != 0u;
+            float2 *slot = img_fb + (long)(w.slot0 + w.tr0) * slot_stride;
             const float2 *pq = pos + w.tr0 * kThreads + threadIdx.x;
             for (int tr = w.tr0; tr <= w.tr1; ++tr, slot += slot_stride, pq += kThreads) {
-                const float nts = 1.0f - div_const(fabsf((float)tr - e.x), w.fdelta, w.rdelta);   // loss/flow.py:94-95
-                splat_inside_1hot(slot, p.ig, *pq, nts);
+                const float nts = 1.0f - div_const(fabsf((float)tr - ts), w.fdelta, w.rdelta);   // loss/flow.py:94-95
+                splat_inside_1hot_warp(slot, p.ig, *pq, nts, pol, on, lane, key_base);
             }
         }
         return;
     }
+    if (!has) return;
     for (int s = 0; s < p.sc.S; ++s) {
         if (!((has >> s) & 1u)) continue;
         const WinS w = sw[s];
@@ -193,34 +200,83 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
     cx_ = gpx + dt * (dvy_dx * gpy + dvx_dx * gpx);
 }
 
+// step_bwd for a whole warp: the two tap-row reductions of neighbouring lanes that hit the same slot of the same
+// flow-gradient map are merged before they leave the SM (merge_equal_neighbours).  `on` = this lane has a gradient to
+// push through the step; the others only take part in the shuffles.  A row is reduced when its merged values are not all
+// zero: a row outside the map (or with zero weights) carries zeros in every lane of the cell, and adding zeros is a no-op.
+// Must be called by all 32 lanes.  Non-deterministic mode only.
+__device__ __forceinline__ void step_bwd_warp(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
+                                              float sx, float dt, float gpy, float gpx, float &cy_, float &cx_, bool on, unsigned lane,
+                                              unsigned key_base /* sample * map size */) {
+    if (on && !inside(sy, sx, r)) {                 // an event whose own location lies outside the sensor: generic sample, not merged
+        step_bwd<false>(map, gmap, r, g, sy, sx, dt, gpy, gpx, cy_, cx_);
+        on = false;
+    }
+    float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    unsigned off = 0;
+    if (on) {
+        Taps tp;
+        sample_flow_inside<true>(map, r, sy, sx, &tp);
+        const int phase = tp.x0 & 1;
+        off = (unsigned)(phase * (int)g.plane + tp.y0 * g.Wp + tp.x0 + phase);
+        const float c0 = dt * tp.w[0], c1 = tp.ok[1] ? dt * tp.w[1] : 0.0f;       // taps_red's coefficients
+        const float c2 = tp.ok[2] ? dt * tp.w[2] : 0.0f, c3 = tp.ok[3] ? dt * tp.w[3] : 0.0f;
+        v[0] = c0 * gpx; v[1] = c0 * gpy; v[2] = c1 * gpx; v[3] = c1 * gpy;
+        v[4] = c2 * gpx; v[5] = c2 * gpy; v[6] = c3 * gpx; v[7] = c3 * gpy;
+        const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
+        const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
+        const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
+        const float dvx_dx = (1.0f - tp.ay) * (tp.v[1].x - tp.v[0].x) + tp.ay * (tp.v[3].x - tp.v[2].x);
+        cy_ = gpy + dt * (dvy_dy * gpy + dvx_dy * gpx);
+        cx_ = gpx + dt * (dvy_dx * gpy + dvx_dx * gpx);
+    }
+    const bool gave = merge_equal_neighbours<8>(on ? key_base + off : (0x80000000u | lane), lane, v);
+    if (on && !gave) {
+        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) red_add_v4(gmap + off, v[0], v[1], v[2], v[3]);
+        if (v[4] != 0.0f || v[5] != 0.0f || v[6] != 0.0f || v[7] != 0.0f) red_add_v4(gmap + (off + (unsigned)g.Wp), v[4], v[5], v[6], v[7]);
+    }
+}
+
 // One thread per gradient-carrying event.  Chain positions come from the forward kernel's posbuf
 // (coalesced loads); per node: gather the gradient images at the corners, add what flows back from the
 // next node, reduce into the packed flow-gradient map and step towards the event's own window.
+// The node loops run over the CTA-uniform range of nodes any scale splats for this pass, and (outside the deterministic
+// mode) threads without an event or without a gradient stay in them for the warp-level merge of the reductions.
 template <bool DET>
 __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(const __grid_constant__ CmParams p) {
     __shared__ WinS sw[TEF_MAX_SCALES];
     int t, b, row, set; float4 e; float2 m;
     const bool live = locate_sorted(p, t, b, e, m, row, set);
     build_windows(p, t, sw);
-    if (!live) return;
+    if (DET && !live) return;
     const int f = blockIdx.y;
     const long HW = 2 * p.res.fplane;                              // float2 elements per (pass, sample) flow map
     const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
     const long gmap_sz = (DET ? 4 : 2) * p.ig.plane;               // float2 elements per (pass, sample) gradient map
     float2 *gflow_f = p.gflow + (long)f * p.P * p.B * gmap_sz;
-    const float ts = e.x, y0 = e.y, x0 = e.z;
-    const uint32_t alive = p.alivebuf[(long)f * p.rows_grad + row];
-    const float2 *pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
-
-    // scales whose sub-window takes this event, and the range of nodes that receive an image gradient
-    const uint32_t has = active_scales(p, sw, alive);
-    if (!has) return;
+    uint32_t alive = 0, has = 0;
+    const float2 *pb = nullptr;
+    float ts = 0.f, y0 = 0.f, x0 = 0.f;
+    if (live) {
+        ts = e.x; y0 = e.y; x0 = e.z;
+        alive = p.alivebuf[(long)f * p.rows_grad + row];
+        pb = p.posbuf + (long)f * (p.P + 1) * p.rows_grad + row;
+        // scales whose sub-window takes this event
+        has = active_scales(p, sw, alive);
+    } else {
+        b = 0; m = make_float2(0.f, 0.f);
+    }
+    if (DET && !has) return;
+    const bool act = has != 0u;
+    // nodes that receive an image gradient at some scale: the CTA-uniform range the forward kernel kept
     int lo_node = p.P + 1, hi_node = -1;
     for (int s = 0; s < p.sc.S; ++s)
-        if ((has >> s) & 1u) { lo_node = min(lo_node, sw[s].tr0); hi_node = max(hi_node, sw[s].tr1); }
+        if (sw[s].valid) { lo_node = min(lo_node, sw[s].tr0); hi_node = max(hi_node, sw[s].tr1); }
     // gradient images: [phase][pol][H][Wp] float2 per slot -- in place in img, or gimg in deterministic mode
     const long gslot = 4 * p.ig.plane;
     const float2 *img_fb = (DET ? p.gimg : p.img) + ((long)f * p.B + b) * p.nslots * gslot;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned key_base = (unsigned)b * (unsigned)gmap_sz;
 
     // scale 0 (the only one in every shipped config) is kept in registers: the window table is otherwise re-read from
     // shared memory at every node (14 M broadcast loads per launch, 11 % of the kernel's L1TEX wavefronts)
@@ -246,19 +302,19 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         const float2 *pq = pb + (long)tr * p.rows_grad;                  // position of node tr; one row_grad back: node tr-1
         const float2 *map = flow_f + (long)(tr - 1) * map_stride + (long)b * HW;
         float2 *gmap = gflow_f + (long)(tr - 1) * gmap_stride + (long)b * gmap_sz;
-        float2 q = (tr >= t + 1) ? __ldcs(pq) : make_float2(0.f, 0.f);
+        float2 q = (act && tr >= t + 1) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr >= t + 1; --tr, pq -= p.rows_grad, map -= map_stride, gmap -= gmap_stride) {
             const bool first = (tr - 1 == t);
-            const float2 src = first ? make_float2(x0, y0) : __ldcs(pq - p.rows_grad);
-            const bool al = ((alive >> tr) & 1u) != 0;
+            const float2 src = first ? make_float2(x0, y0) : (act ? __ldcs(pq - p.rows_grad) : make_float2(0.f, 0.f));
+            const bool al = ((alive >> tr) & 1u) != 0;                   // alive == 0 without an event
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
             const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
             cy_ = 0.f; cx_ = 0.f;
-            if (gpy != 0.f || gpx != 0.f) {
-                const float dt = first ? ((float)tr - ts) : 1.0f;
-                step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
-            }
+            const bool on = gpy != 0.f || gpx != 0.f;
+            const float dt = first ? ((float)tr - ts) : 1.0f;
+            if (!DET) step_bwd_warp(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
+            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
             q = src;
         }
     }
@@ -269,19 +325,19 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         const float2 *pq = pb + (long)tr * p.rows_grad;
         const float2 *map = flow_f + (long)tr * map_stride + (long)b * HW;
         float2 *gmap = gflow_f + (long)tr * gmap_stride + (long)b * gmap_sz;
-        float2 q = (tr <= t) ? __ldcs(pq) : make_float2(0.f, 0.f);
+        float2 q = (act && tr <= t) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr <= t; ++tr, pq += p.rows_grad, map += map_stride, gmap += gmap_stride) {
             const bool first = (tr == t);
-            const float2 src = first ? make_float2(x0, y0) : __ldcs(pq + p.rows_grad);
+            const float2 src = first ? make_float2(x0, y0) : (act ? __ldcs(pq + p.rows_grad) : make_float2(0.f, 0.f));
             const bool al = ((alive >> tr) & 1u) != 0;
             float gy = 0.f, gx = 0.f;
             if (al) node_grad(tr, q, gy, gx);
             const float gpy = al ? gy + cy_ : 0.f, gpx = al ? gx + cx_ : 0.f;
             cy_ = 0.f; cx_ = 0.f;
-            if (gpy != 0.f || gpx != 0.f) {
-                const float dt = first ? ((float)tr - ts) : -1.0f;
-                step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
-            }
+            const bool on = gpy != 0.f || gpx != 0.f;
+            const float dt = first ? ((float)tr - ts) : -1.0f;
+            if (!DET) step_bwd_warp(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
+            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
             q = src;
         }
     }

@@ -23,11 +23,26 @@ __global__ void __launch_bounds__(kThreads) mb_red_kernel(float4 *buf, uint32_t 
         if (mode == 2) a = (warp_base + lane + (uint32_t)i * 32u) & (slots - 1);
         else if (mode == 3) a = (warp_base + (uint32_t)i) & (slots - 1);
         else if (mode >= 4) {
-            const uint32_t g = mode == 6 ? (lane >> 2) : (lane >> 1);
+            const uint32_t g = mode == 6 ? (lane >> 2) : (lane >> 1);       // modes 4, 5, 7: pairs
             uint32_t h = (warp_base * 31u + g * 2654435761u + (uint32_t)i * 40503u);      // same value for the lanes of a group
             h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
             const uint32_t slot = (warp_base + (h & 255u) + (uint32_t)i * 64u) & (slots - 1);
             a = mode == 5 ? ((slot & ~1u) | (lane & 1u)) : slot;
+        }
+        if (mode >= 7) {
+            // software merge of adjacent equal addresses, as a kernel would do it: mode 7 = pairs always equal (upper bound of the
+            // benefit), mode 8 = random slots, nothing to merge (pure cost of the shuffles)
+            if (mode == 8) a = (warp_base + (r & 255u) + (uint32_t)i * 64u) & (slots - 1);
+            float v0 = 1.0f + (float)lane, v1 = 0.5f, v2 = 0.25f * (float)i, v3 = 0.125f;
+            const uint32_t nk = __shfl_down_sync(0xffffffffu, a, 1);
+            const float n0 = __shfl_down_sync(0xffffffffu, v0, 1), n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+            const float n2 = __shfl_down_sync(0xffffffffu, v2, 1), n3 = __shfl_down_sync(0xffffffffu, v3, 1);
+            const bool take = !(lane & 1u) && nk == a;                  // even lane absorbs its odd neighbour
+            const uint32_t taken = __ballot_sync(0xffffffffu, take);
+            const bool gone = (lane & 1u) && ((taken >> (lane - 1u)) & 1u);
+            if (take) { v0 += n0; v1 += n1; v2 += n2; v3 += n3; }
+            if (!gone) red_add_v4(reinterpret_cast<float2 *>(buf + a), v0, v1, v2, v3);
+            continue;
         }
         red_add_v4(reinterpret_cast<float2 *>(buf + a), 1.0f, 0.5f, 0.25f, 0.125f);
     }
