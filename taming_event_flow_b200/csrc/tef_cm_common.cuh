@@ -354,25 +354,36 @@ __device__ __forceinline__ void splat_inside_1hot(float2 *__restrict__ pol_plane
 
 // Warp-level merge of equal reduction addresses (DESIGN.md decision 13: the reduction path charges one sector per lane
 // whatever the addresses, and tile-sorted events put equal addresses on neighbouring lanes).  `key` identifies the 16-byte
-// slot a lane is about to reduce into (lanes without work pass a key no other lane has).  One round: inside every run of
-// equal keys the lanes of odd rank hand their values to the lane before them.  Returns true for a lane that gave its
-// values away; the receivers' v[] hold the sums.  Must be called by all 32 lanes.
+// slot a lane is about to reduce into (lanes without work pass a key no other lane has).  Inside every run of equal keys
+// the lanes of odd rank hand their values to the lane before them; further rounds (TEF_MERGE_ROUNDS) repeat that among the
+// survivors at distance 2, 4, ...  Returns true for a lane that gave its values away; the receivers' v[] hold the sums.
+// Must be called by all 32 lanes.
+#ifndef TEF_MERGE_ROUNDS
+#define TEF_MERGE_ROUNDS 1
+#endif
 template <int NV>
 __device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned lane, float (&v)[NV]) {
     const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool same = lane > 0u && key == prev;
     const unsigned heads = __ballot_sync(0xffffffffu, !same);               // first lane of every run
     if (heads == 0xffffffffu) return false;                                // nothing to merge in this warp (uniform branch)
-    const unsigned start = 31u - (unsigned)__clz(heads & (0xffffffffu >> (31u - lane)));
-    const bool give = ((lane - start) & 1u) != 0u;
-    const unsigned givers = __ballot_sync(0xffffffffu, give);
-    const bool recv = lane < 31u && ((givers >> (lane + 1u)) & 1u) != 0u;   // the next lane is in my run and has odd rank
+    const unsigned rank = lane - (31u - (unsigned)__clz(heads & (0xffffffffu >> (31u - lane))));
+    bool gave = false;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const float n = __shfl_down_sync(0xffffffffu, v[k], 1);
-        if (recv) v[k] += n;
+    for (int r = 0; r < TEF_MERGE_ROUNDS; ++r) {                           // round r: rank d (mod 2d) hands over to rank 0 (mod 2d), d = 2^r
+        const unsigned d = 1u << r;
+        const bool give = (rank & (2u * d - 1u)) == d;
+        const unsigned givers = __ballot_sync(0xffffffffu, give);
+        if (r > 0 && givers == 0u) break;                                  // no run longer than d (uniform branch)
+        const bool recv = lane + d < 32u && ((givers >> (lane + d)) & 1u) != 0u;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float n = __shfl_down_sync(0xffffffffu, v[k], d);
+            if (recv) v[k] += n;
+        }
+        gave |= give;
     }
-    return give;
+    return gave;
 }
 
 // splat_inside_1hot for a whole warp, with equal slots of neighbouring lanes merged before they leave the SM.  `on` = this
@@ -433,6 +444,42 @@ __device__ __forceinline__ void iwe_grad(const float2 *__restrict__ slot_base, c
         }
         if (c.okx[0]) { gy += gl * dy[ky] * c.wx[0]; gx += gl * c.wy[ky] * dx[0]; }
         if (c.okx[1]) { gy += gr * dy[ky] * c.wx[1]; gx += gr * c.wy[ky] * dx[1]; }
+    }
+}
+
+// iwe_grad<true> for a one-hot {0,1} polarity mask and a position (x, y) that satisfies inside(): same values, fewer
+// instructions (the backward kernel is the one that is bound by instruction issue).
+//  * the mask product is x * 1 == x and only the event's polarity plane is read (`pol_plane` = slot base + polarity * plane);
+//  * d1() with the signs known: v - floor(v) is in [0, 1), so the top / left weight is positive and its derivative is
+//    -1 for v > floor(v) and -0 on the pixel centre; floor(v + 1) >= floor(v) + 1 > v, so the bottom / right difference is
+//    negative and the derivative is +1, +1/2 on the tie (weight exactly 0) and 0 beyond it;
+//  * a bottom row inside the image is read at row floor(y) + 1: when floor(y + 1) is a row further (y + 1 rounded up across
+//    an integer) the row weight and its derivative are both 0 and any finite row gives the same +-0 contributions.
+__device__ __forceinline__ void iwe_grad_inside_1hot(const float2 *__restrict__ pol_plane, const Res &r, const ImgGeom &g, float2 p /* (x, y) */,
+                                                     float nts, float &gy, float &gx) {
+    const float2 c0 = make_float2(floorf(p.x), floorf(p.y));
+    const float2 p1 = add2(p, bc(1.0f));
+    const float2 c1 = make_float2(floorf(p1.x), floorf(p1.y));
+    const float2 d0 = sub2(p, c0), e1 = sub2(p, c1);
+    const float2 u0 = sub2(bc(1.0f), make_float2(fabsf(d0.x), fabsf(d0.y)));
+    const float2 u1 = sub2(bc(1.0f), make_float2(fabsf(e1.x), fabsf(e1.y)));
+    const float wx0 = fmaxf(0.0f, u0.x), wy0 = fmaxf(0.0f, u0.y), wx1 = fmaxf(0.0f, u1.x), wy1 = fmaxf(0.0f, u1.y);
+    const float dx0 = d0.x > 0.0f ? -1.0f : -0.0f, dy0 = d0.y > 0.0f ? -1.0f : -0.0f;
+    const float dx1 = u1.x > 0.0f ? 1.0f : (u1.x == 0.0f ? 0.5f : 0.0f), dy1 = u1.y > 0.0f ? 1.0f : (u1.y == 0.0f ? 0.5f : 0.0f);
+    const int xl = (int)c0.x, phase = xl & 1;
+    const float4 *row = reinterpret_cast<const float4 *>(pol_plane + (phase * 2 * (int)g.plane + (int)c0.y * g.Wp + xl + phase));
+    const bool okx1 = c1.x <= r.wm1;
+    {
+        const float4 v = __ldg(row);
+        const float gl = v.x + nts * v.y, gr = v.z + nts * v.w;
+        gy += gl * dy0 * wx0; gx += gl * wy0 * dx0;
+        if (okx1) { gy += gr * dy0 * wx1; gx += gr * wy0 * dx1; }
+    }
+    if (c1.y <= r.hm1) {
+        const float4 v = __ldg(row + (g.Wp >> 1));
+        const float gl = v.x + nts * v.y, gr = v.z + nts * v.w;
+        gy += gl * dy1 * wx0; gx += gl * wy1 * dx0;
+        if (okx1) { gy += gr * dy1 * wx1; gx += gr * wy1 * dx1; }
     }
 }
 

@@ -282,10 +282,14 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     // shared memory at every node (14 M broadcast loads per launch, 11 % of the kernel's L1TEX wavefronts)
     const int w0_tr0 = (has & 1u) ? sw[0].tr0 : 1, w0_tr1 = (has & 1u) ? sw[0].tr1 : 0, w0_slot0 = sw[0].slot0;
     const float w0_fdelta = sw[0].fdelta, w0_rdelta = sw[0].rdelta;
+    // the loader's one-hot masks read one polarity plane and skip the mask products
+    const bool onehot = (m.x == 1.0f && m.y == 0.0f) || (m.x == 0.0f && m.y == 1.0f);
+    const float2 *img_pol = img_fb + (m.x != 0.0f ? 0 : p.ig.plane);
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         if (tr >= w0_tr0 && tr <= w0_tr1) {
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), w0_fdelta, w0_rdelta);
-            iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.y, q.x, nts, m, gy, gx);
+            if (onehot) iwe_grad_inside_1hot(img_pol + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q, nts, gy, gx);
+            else iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.y, q.x, nts, m, gy, gx);
         }
         for (int s = 1; s < p.sc.S; ++s) {
             if (!((has >> s) & 1u) || tr < sw[s].tr0 || tr > sw[s].tr1) continue;
