@@ -219,14 +219,18 @@ __device__ __forceinline__ void step_bwd_warp(const float2 *__restrict__ map, fl
         sample_flow_inside<true>(map, r, sy, sx, &tp);
         const int phase = tp.x0 & 1;
         off = (unsigned)(phase * (int)g.plane + tp.y0 * g.Wp + tp.x0 + phase);
-        const float c0 = dt * tp.w[0], c1 = tp.ok[1] ? dt * tp.w[1] : 0.0f;       // taps_red's coefficients
-        const float c2 = tp.ok[2] ? dt * tp.w[2] : 0.0f, c3 = tp.ok[3] ? dt * tp.w[3] : 0.0f;
-        v[0] = c0 * gpx; v[1] = c0 * gpy; v[2] = c1 * gpx; v[3] = c1 * gpy;
-        v[4] = c2 * gpx; v[5] = c2 * gpy; v[6] = c3 * gpx; v[7] = c3 * gpy;
-        const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
-        const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
-        const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
-        const float dvx_dx = (1.0f - tp.ay) * (tp.v[1].x - tp.v[0].x) + tp.ay * (tp.v[3].x - tp.v[2].x);
+        // taps_red's coefficients and values, and step_bwd's Jacobian, on packed fp32x2 arithmetic: same products, rounded
+        // one by one (sums of two products stay scalar: ptxas would contract a packed product into a packed sum)
+        const float2 c01 = mul2(bc(dt), make_float2(tp.w[0], tp.w[1])), c23 = mul2(bc(dt), make_float2(tp.w[2], tp.w[3]));
+        const float c0 = c01.x, c1 = tp.ok[1] ? c01.y : 0.0f, c2 = tp.ok[2] ? c23.x : 0.0f, c3 = tp.ok[3] ? c23.y : 0.0f;
+        const float2 gp = make_float2(gpx, gpy);
+        const float2 r0 = mul2(bc(c0), gp), r1 = mul2(bc(c1), gp), r2 = mul2(bc(c2), gp), r3 = mul2(bc(c3), gp);
+        v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y; v[4] = r2.x; v[5] = r2.y; v[6] = r3.x; v[7] = r3.y;
+        // d(flow)/dy and d(flow)/dx as (x-flow, y-flow) pairs
+        const float2 a20 = sub2(tp.v[2], tp.v[0]), a31 = sub2(tp.v[3], tp.v[1]), a10 = sub2(tp.v[1], tp.v[0]), a32 = sub2(tp.v[3], tp.v[2]);
+        const float2 py0 = mul2(bc(1.0f - tp.ax), a20), py1 = mul2(bc(tp.ax), a31);
+        const float2 px0 = mul2(bc(1.0f - tp.ay), a10), px1 = mul2(bc(tp.ay), a32);
+        const float dvx_dy = py0.x + py1.x, dvy_dy = py0.y + py1.y, dvx_dx = px0.x + px1.x, dvy_dx = px0.y + px1.y;
         cy_ = gpy + dt * (dvy_dy * gpy + dvx_dy * gpx);
         cx_ = gpx + dt * (dvy_dx * gpy + dvx_dx * gpx);
     }
