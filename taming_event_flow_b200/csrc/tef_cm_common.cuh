@@ -322,36 +322,6 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
     }
 }
 
-// splat<true, false> for a one-hot {0,1} polarity mask -- the only kind the reference's loader produces
-// (dataloader/base.py:264-278) -- on packed fp32x2 arithmetic, for a position (x, y) that satisfies inside().
-// Same values and the same set of reductions as splat():
-//  * the in-image tests of the bottom / right corners are implied by the weights: floor(v + 1) > size - 1 needs
-//    v + 1 >= size, i.e. |v - corner| >= 1, whose clamped weight is an exact 0;
-//  * v - floor(v) is exact and < 1, so the top / left weights are >= 2^-24: the top row always has a non-zero weight
-//    (never skipped), and the bottom row has two zero weights exactly when its row weight is 0 (products of weights
-//    >= 2^-24 do not underflow);
-//  * a bottom row that is not skipped has floor(y + 1) == floor(y) + 1.
-// `pol_plane` = slot base + polarity * plane.
-__device__ __forceinline__ void splat_inside_1hot(float2 *__restrict__ pol_plane, const ImgGeom &g, float2 p /* (x, y) */, float nts) {
-    const float2 c0 = make_float2(floorf(p.x), floorf(p.y));
-    const float2 p1 = add2(p, bc(1.0f));
-    const float2 c1 = make_float2(floorf(p1.x), floorf(p1.y));
-    const float2 d0 = sub2(p, c0), d1_ = sub2(p, c1);
-    const float2 u0 = sub2(bc(1.0f), make_float2(fabsf(d0.x), fabsf(d0.y)));      // utils/iwe.py:96-99
-    const float2 u1 = sub2(bc(1.0f), make_float2(fabsf(d1_.x), fabsf(d1_.y)));
-    const float2 wx = make_float2(fmaxf(0.0f, u0.x), fmaxf(0.0f, u1.x));          // (left, right)
-    const float wy0 = fmaxf(0.0f, u0.y), wy1 = fmaxf(0.0f, u1.y);
-    const int xl = (int)c0.x, phase = xl & 1;
-    const unsigned off = (unsigned)(phase * 2 * (int)g.plane + (int)c0.y * g.Wp + xl + phase);      // a slot is far below 2^31 elements
-    char *base = reinterpret_cast<char *>(pol_plane);
-    const float2 a = mul2(bc(wy0), wx);                                            // (w_left, w_right) of the top row
-    red_add_v4(reinterpret_cast<float2 *>(base + (size_t)off * 8u), a.x, a.x * nts, a.y, a.y * nts);
-    if (wy1 != 0.0f) {
-        const float2 b = mul2(bc(wy1), wx);
-        red_add_v4(reinterpret_cast<float2 *>(base + (size_t)(off + (unsigned)g.Wp) * 8u), b.x, b.x * nts, b.y, b.y * nts);
-    }
-}
-
 // Warp-level merge of equal reduction addresses (DESIGN.md decision 13: the reduction path charges one sector per lane
 // whatever the addresses, and tile-sorted events put equal addresses on neighbouring lanes).  `key` identifies the 16-byte
 // slot a lane is about to reduce into (lanes without work pass a key no other lane has).  Inside every run of equal keys
@@ -386,10 +356,18 @@ __device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned la
     return gave;
 }
 
-// splat_inside_1hot for a whole warp, with equal slots of neighbouring lanes merged before they leave the SM.  `on` = this
-// lane has an event to splat (the others only take part in the shuffles); `plane_sel` = polarity (0 / 1).  Both image rows
-// of a splat share one key (equal top slots imply equal bottom slots); a lane whose own bottom row has weight 0 carries
-// zeros there, and the bottom row is reduced when the merged row weight is non-zero (then the row exists: the
+// splat<true, false> for the events of a whole warp with one-hot {0,1} polarity masks -- the only kind the reference's loader
+// produces (dataloader/base.py:264-278) -- on packed fp32x2 arithmetic, for positions (x, y) that satisfy inside(), with equal
+// slots of neighbouring lanes merged before they leave the SM.  Same values as splat():
+//  * the in-image tests of the bottom / right corners are implied by the weights: floor(v + 1) > size - 1 needs
+//    v + 1 >= size, i.e. |v - corner| >= 1, whose clamped weight is an exact 0;
+//  * v - floor(v) is exact and < 1, so the top / left weights are >= 2^-24: the top row always has a non-zero weight
+//    (never skipped), and the bottom row has two zero weights exactly when its row weight is 0 (products of weights
+//    >= 2^-24 do not underflow);
+//  * a bottom row with a non-zero weight has floor(y + 1) == floor(y) + 1.
+// `on` = this lane has an event to splat (the others only take part in the shuffles); `plane_sel` = polarity (0 / 1).  Both
+// image rows of a splat share one key (equal top slots imply equal bottom slots); a lane whose own bottom row has weight 0
+// carries zeros there, and the bottom row is reduced when the merged row weight is non-zero (then the row exists: the
 // contributor that supplied it shares the cell).  Lanes of one warp may belong to different samples (same slot offsets,
 // different images), hence `key_base`.  Must be called by all 32 lanes.
 __device__ __forceinline__ void splat_inside_1hot_warp(float2 *__restrict__ slot_base, const ImgGeom &g, float2 p /* (x, y) */, float nts,
