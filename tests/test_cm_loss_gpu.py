@@ -395,7 +395,7 @@ def test_warp_merge_with_heavy_pixel_reuse_and_sample_boundaries(B, H, W, N):
     py = torch.randint(1, H - 2, (3,), generator=gen).float()
     flows, events, masks, d_events, d_masks = [], [], [], [], []
     for t in range(P):
-        flows.append([torch.zeros(B, 2, H, W), (torch.rand(B, 2, H, W, generator=gen) - 0.5) * 0.6])
+        flows.append([torch.zeros(B, 2, H, W), ((torch.rand(1, 2, H, W, generator=gen) - 0.5) * 0.6).repeat(B, 1, 1, 1).contiguous()])   # same maps in every sample
         for evs, mks, n in ((events, masks, N), (d_events, d_masks, max(N // 3, 1))):
             which = torch.randint(0, 3, (n,), generator=gen)
             ts, _ = torch.sort(torch.rand(n, generator=gen).mul(4).floor().div(4))      # only four distinct timestamps
@@ -414,8 +414,11 @@ def test_warp_merge_with_heavy_pixel_reuse_and_sample_boundaries(B, H, W, N):
         l, _ = rel_err(g["iwe"][:, b], g["iwe"][:, 0])
         assert l < TOL
     assert abs(g["loss"] - o["loss"]) <= TOL * abs(o["loss"])
-    # up to several hundred events per pixel: the fp32 reference itself is order-sensitive there, so
-    # the gradient is held to 1e-5 in L2 and 1e-4 in isolated pixels
-    linf, l2 = rel_err(g["gflow"], o["gflow"])
-    assert linf < 10 * TOL and l2 < TOL, ("grad", linf, l2)
+    # up to several hundred events per pixel with cancelling gradients: the fp32 reference arithmetic itself is 3e-5 ... 5e-5
+    # (L2) away from its fp64 run on these inputs, i.e. order-sensitive beyond 1e-5, so the gradient is
+    # triangulated against fp64: the CUDA path may be at most twice as far from fp64 as the fp32 oracle is
+    o64 = orc.iterative(orc.make_cfg(B, H, W, P, F, 1, "two", True), flows, events, masks, d_events, d_masks, np.float64, want_grad=True)
+    ref_linf, ref_l2 = rel_err(o["gflow"], o64["gflow"])
+    linf, l2 = rel_err(g["gflow"], o64["gflow"])
+    assert linf <= 2 * ref_linf + TOL and l2 <= 2 * ref_l2 + TOL, ("grad", linf, l2, ref_linf, ref_l2)
 
