@@ -366,12 +366,15 @@ static size_t chain_smem(const CmParams &p) { return sizeof(float2) * (size_t)(p
 
 static int launch_fwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
-        static bool attr = false;
-        if (!attr) {
+        // the opt-in to more than 48 KB of dynamic shared memory (P >= 23) is a per-device attribute of the function
+        static unsigned long long attr_done = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
             const int mx = (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads);
             cudaFuncSetAttribute(iter_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             cudaFuncSetAttribute(iter_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            attr = true;
+            if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
         }
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_FWD, st);
