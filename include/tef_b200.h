@@ -12,6 +12,11 @@
  *     owned and allocated by the caller, nothing is allocated inside;
  *   - all arithmetic is fp32; tensors are contiguous, row-major, laid out as the
  *     reference's tensors unless stated;
+ *   - image and flow-gradient sums use red.global.add.f32, which sm_100a implements as REDG...F32.FTZ: a
+ *     DENORMAL partial sum or addend is flushed to zero where the CPU reference keeps it.  Weights are products
+ *     of two factors >= 2^-24, so an addend is >= 2^-48 and never denormal; flow-gradient addends can be, at
+ *     magnitudes (< 1.2e-38) far below the 1e-5 norm-relative tolerance.  The deterministic mode (integer
+ *     reductions) has no flush;
  *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
  *   - return value: 0 on success, a positive cudaError_t from the launch, or a
  *     negative TEF_E* argument error.  tef_strerror() explains both.
@@ -81,6 +86,9 @@ typedef struct tef_cm_desc {
      gradient-carrying rows, floats in posbuf, padded row length Wp, chunks per image (acc_sum / acc_nnz),
      floats in gimg } */
 int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out);
+/* number of image slots (temporal scale x sub-window x reference time, loss/flow.py:657-668) of the configuration in `d`,
+   or the negative TEF_E* code the forward call would return for it */
+int tef_cm_num_slots(const tef_cm_desc *d, int linear);
 
 /* Iterative.update / Linear.update, event part (loss/flow.py:456-473, :246-263):
    ts += pass_index IN PLACE in the caller's [B,n,4] tensor, then (ts | ts_override), y, x, p
@@ -115,6 +123,12 @@ typedef struct tef_update_desc {
                                               (k*P + t)*B*tiles*128 (the layout tef_*_forward expects with hist_done = 1) */
     int hist;                              /* 1: count this pass' events into sort_bins            */
     int zero_bins;                         /* 1: clear sort_bins first (first update of a window)  */
+    /* strided[k] = 1: events[k] / masks[k] are NOT contiguous rows; element (b, row, col) of the [B][n][4] event tensor is at
+       ev_strides[k][0]*b + ev_strides[k][1]*row + ev_strides[k][2]*col floats (masks likewise, [B][n][2]) -- the transposed
+       views the reference's custom_collate returns (dataloader/base.py:414-431); rows[k] must be a multiple of B */
+    int strided[2];
+    long ev_strides[2][3];
+    long mk_strides[2][3];
 } tef_update_desc;
 int tef_update_pass(const tef_update_desc *u, void *stream);
 
@@ -158,10 +172,14 @@ int tef_deblur_events(const float *flow, const float *events, const float *pol, 
 /* ------------------------------------------------------------------------- */
 /* dataloader/encodings.py                                                    */
 /* ------------------------------------------------------------------------- */
-/* events_to_image (:8-29): img [H][W] zeroed inside; accumulate=0 keeps the reference's last-writer-wins put */
-int tef_events_to_image(const float *xs, const float *ys, const float *ps, float *img, long n, int H, int W, int accumulate, void *stream);
+/* `oob` (device int, may be NULL) is set to 1 when an event's truncated (and, if negative, wrapped) coordinates fall outside
+   the sensor -- where the reference's index_put_ raises IndexError (:23-27); such events are skipped.  The caller zeroes it. */
+/* events_to_image (:8-29): img [H][W] initialised inside.  accumulate=0 is the reference's plain put: the LAST event of a
+   pixel wins (the order of its CPU kernel), computed deterministically in two passes (highest event index per pixel first) */
+int tef_events_to_image(const float *xs, const float *ys, const float *ps, float *img, long n, int H, int W, int accumulate, int *oob,
+                        void *stream);
 /* events_to_channels (:59-81): out [2][H][W] */
-int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, void *stream);
+int tef_events_to_channels(const float *xs, const float *ys, const float *ps, float *out, long n, int H, int W, int *oob, void *stream);
 /* batched events_to_channels over the loader's zero-padded [B][N][4] (ts, y, x, p) rows: out [B][2][H][W] */
 int tef_events_to_channels_batched(const float *events, float *out, int B, int N, int H, int W, void *stream);
 /* get_hot_event_mask: NOT in this reference (north_star names it) -- "parity unpinned".  Implements the
@@ -169,7 +187,8 @@ int tef_events_to_channels_batched(const float *events, float *out, int B, int N
    event_rate [H][W] is zeroed and masked while it exceeds max_rate.  event_rate is modified in place like there. */
 int tef_get_hot_event_mask(float *event_rate, float *mask, int H, int W, int idx, int max_px, int min_obvs, float max_rate, void *stream);
 /* events_to_voxel (:32-56): out [bins][H][W] */
-int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, void *stream);
+int tef_events_to_voxel(const float *xs, const float *ys, const float *ts, const float *ps, float *out, long n, int bins, int H, int W, int *oob,
+                        void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* dataloader/base.py -- the loader -> loss contract          */
@@ -233,9 +252,14 @@ int tef_val_forward_prop_flow(const float *mapsx, const float *mapsy, int first,
 int tef_val_trajectory_step(const float *mapx, const float *mapy, float *idx, float *out_mask, float *accx, float *accy, int H, int W,
                             void *stream);
 
-/* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers, 2 = 16-byte gathers;
+/* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers, 2 = 16-byte gathers,
+   4 = 2x2 neighbourhood fetches of tile-sorted positions (mode 0: two 16-byte gathers in the dual-phase layout, 1: one 32-byte gather);
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */
 int tef_microbench(int kind, int mode, void *buf, long bytes, int iters, long *ops, void *stream);
+/* the shared-memory counterpart (north_star's smem tiles): 16-byte updates accumulated in a CTA-private shared-memory patch with
+   shared-memory atomics (atom 0 = fp32 compare-and-swap loop, 1 = native u32 fixed point, 2 = u64 fixed point), flushed with coalesced
+   red.v4 every k updates per thread; patch_slots = 16-byte slots per patch; pattern 0 = random slots, 1 = tile-sorted-like */
+int tef_microbench_smem(int atom, int patch_slots, int k, int pattern, void *buf, long bytes, int iters, long *ops, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* launch accounting / per-kernel timing (used by bench.py for gpu_launches   */

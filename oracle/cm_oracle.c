@@ -7,7 +7,7 @@
  *
  * Parity pin: the reference ships no tests or golden vectors (SURVEY.md §4,
  * §8c); this oracle is pinned against the reference itself, imported live in
- * the build container, by tests/test_oracle_vs_reference.py and through the
+ * the build container, by tests/test_oracle_vs_reference_live.py and through the
  * committed vectors under tests/golden/ (made by tests/golden/make_golden.py).
  */
 #include <math.h>
@@ -15,7 +15,12 @@
 #include <string.h>
 #include "cm_oracle.h"
 
+/* ACC = type of the image / flow-gradient accumulators.  ACC == REAL restates the reference (its sums are fp32 in
+ * index order).  The third instance below (suffix _f32x: fp32 per-event arithmetic, double accumulators, each sum
+ * rounded to fp32 once) is NOT the reference: it is the summation-order-free yardstick the tests use to show that what
+ * separates the CUDA path from the reference is the order of fp32 additions and nothing else. */
 #define REAL float
+#define ACC float
 #define FN(n) n##_f32
 #define R_FMA fmaf
 #define R_FLOOR floorf
@@ -23,6 +28,23 @@
 #define R_RINT rintf
 #include "cm_oracle_impl.h"
 #undef REAL
+#undef ACC
+#undef FN
+#undef R_FMA
+#undef R_FLOOR
+#undef R_FABS
+#undef R_RINT
+
+#define REAL float
+#define ACC double
+#define FN(n) n##_f32x
+#define R_FMA fmaf
+#define R_FLOOR floorf
+#define R_FABS fabsf
+#define R_RINT rintf
+#include "cm_oracle_impl.h"
+#undef REAL
+#undef ACC
 #undef FN
 #undef R_FMA
 #undef R_FLOOR
@@ -30,6 +52,7 @@
 #undef R_RINT
 
 #define REAL double
+#define ACC double
 #define FN(n) n##_f64
 #define R_FMA fma
 #define R_FLOOR floor

@@ -98,9 +98,12 @@ _ERRORS = {
 }
 
 
-def _run(kind, cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, want_nodes):
+def _run(kind, cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, want_nodes, exact_sums=False):
     L = lib()
     sfx = "f32" if dtype == np.float32 else "f64"
+    if exact_sums:
+        assert dtype == np.float32, "exact_sums: fp32 per-event arithmetic with double accumulators"
+        sfx = "f32x"
     P, F, B, H, W = cfg.P, cfg.F, cfg.B, cfg.H, cfg.W
     assert len(flows) >= P and len(events) >= P
     flow = np.empty((F, P, B, 2, H, W), dtype)
@@ -141,14 +144,17 @@ def _run(kind, cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, w
     return out
 
 
-def iterative(cfg, flows, events, masks, d_events, d_masks, dtype=np.float32, want_grad=True, want_iwe=False, want_nodes=False):
-    """``Iterative`` loss forward (+ analytic backward), upstream ``loss/flow.py:415-746``."""
-    return _run("iterative", cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, want_nodes)
+def iterative(cfg, flows, events, masks, d_events, d_masks, dtype=np.float32, want_grad=True, want_iwe=False, want_nodes=False, exact_sums=False):
+    """``Iterative`` loss forward (+ analytic backward), upstream ``loss/flow.py:415-746``.
+
+    ``exact_sums=True`` is NOT the reference: same fp32 per-event arithmetic, but every image pixel and flow-gradient tap is
+    summed in double and rounded to fp32 once -- the yardstick that is free of any fp32 summation order."""
+    return _run("iterative", cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, want_nodes, exact_sums)
 
 
-def linear(cfg, flows, events, masks, d_events, d_masks, dtype=np.float32, want_grad=True, want_iwe=False):
+def linear(cfg, flows, events, masks, d_events, d_masks, dtype=np.float32, want_grad=True, want_iwe=False, exact_sums=False):
     """``Linear`` loss forward (+ analytic backward), upstream ``loss/flow.py:216-412``."""
-    return _run("linear", cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, False)
+    return _run("linear", cfg, flows, events, masks, d_events, d_masks, dtype, want_grad, want_iwe, False, exact_sums)
 
 
 # ---------------------------------------------------------------------------

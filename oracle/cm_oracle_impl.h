@@ -17,7 +17,7 @@
  * the reference's eager CPU PyTorch path operation by operation; the build
  * uses -ffp-contract=off so that the only fused multiply-adds are the explicit
  * ones (ATen's CPU grid_sample accumulates its four taps as an FMA chain --
- * established bit-exactly in tests/test_oracle_vs_reference.py).
+ * established bit-exactly in tests/test_primitives_vs_reference_live.py and tests/test_oracle_vs_reference_live.py).
  */
 
 /* ------------------------------------------------------------------------ */
@@ -296,7 +296,8 @@ int FN(orc_iterative)(const orc_cfg *c,
     }
     const size_t img_sz = (size_t)B * nslots * 4 * HW;
     REAL *img = (REAL *)malloc(sizeof(REAL) * img_sz);       /* grad+detached sums: cnt+,cnt-,ts+,ts-   */
-    REAL *dimg = (REAL *)malloc(sizeof(REAL) * img_sz);      /* detached partial images                 */
+    ACC *aimg = (ACC *)malloc(sizeof(ACC) * img_sz);         /* partial images of the gradient set ...  */
+    ACC *adimg = (ACC *)malloc(sizeof(ACC) * img_sz);        /* ... and of the detached set (ACC = REAL: the reference's sums) */
     double *nnz = (double *)malloc(sizeof(double) * (size_t)B * nslots);
     REAL *gst[2] = { NULL, NULL };                           /* per-node g' of fwd / bwd chain [P+1][E][2] */
     if (gflow) for (int k = 0; k < 2; ++k)
@@ -335,8 +336,8 @@ int FN(orc_iterative)(const orc_cfg *c,
             const orc_slot *sl = &slots[q];
             for (int k = 0; k < 2; ++k) {
                 const FN(evset) *s = &sets[k]; const long E = s->E;
-                REAL *im = (k == 0 ? img : dimg) + ((size_t)b * nslots + q) * 4 * HW;
-                memset(im, 0, sizeof(REAL) * 4 * HW);
+                ACC *im = (k == 0 ? aimg : adimg) + ((size_t)b * nslots + q) * 4 * HW;
+                memset(im, 0, sizeof(ACC) * 4 * HW);
                 for (int corner = 0; corner < 4; ++corner)
                     for (int t = 0; t < P; ++t) {
                         if (!FN(slot_takes)(sl, t)) continue;
@@ -350,14 +351,14 @@ int FN(orc_iterative)(const orc_cfg *c,
                             REAL nts = (REAL)1 - R_FABS((REAL)sl->tref - s->ts[e]) / (REAL)sl->delta;
                             REAL w = cr.w[corner], wt = w * nts;
                             long px = cr.pix[corner];
-                            im[0 * HW + px] += w * mp; im[1 * HW + px] += w * mn;
-                            im[2 * HW + px] += wt * mp; im[3 * HW + px] += wt * mn;
+                            im[0 * HW + px] += (ACC)(REAL)(w * mp); im[1 * HW + px] += (ACC)(REAL)(w * mn);
+                            im[2 * HW + px] += (ACC)(REAL)(wt * mp); im[3 * HW + px] += (ACC)(REAL)(wt * mn);
                         }
                     }
             }
             REAL *im = img + ((size_t)b * nslots + q) * 4 * HW;
-            const REAL *di = dimg + ((size_t)b * nslots + q) * 4 * HW;
-            for (size_t i = 0; i < 4 * HW; ++i) im[i] = im[i] + di[i];
+            const ACC *ai = aimg + ((size_t)b * nslots + q) * 4 * HW, *di = adimg + ((size_t)b * nslots + q) * 4 * HW;
+            for (size_t i = 0; i < 4 * HW; ++i) im[i] = (REAL)(ai[i] + di[i]);       /* loss/flow.py:725-726 */
         }
         if (iwe_out) {
             for (int b = 0; b < B; ++b)
@@ -473,6 +474,7 @@ int FN(orc_iterative)(const orc_cfg *c,
             for (int p = 0; p < P; ++p) for (int b = 0; b < B; ++b) {
                 const REAL *mx = maps + ((size_t)p * B + b) * 2 * HW, *my = mx + HW;
                 REAL *gmx = gf + ((size_t)p * B + b) * 2 * HW, *gmy = gmx + HW;
+                ACC *amx = (ACC *)calloc(2 * HW, sizeof(ACC)), *amy = amx + HW;     /* this map's sums (ACC = REAL: the reference's) */
                 for (int dir = 0; dir < 2; ++dir) {
                     int t0 = dir == 0 ? 0 : p, t1 = dir == 0 ? p : P - 1;
                     int node = dir == 0 ? p + 1 : p;
@@ -489,18 +491,20 @@ int FN(orc_iterative)(const orc_cfg *c,
                         const int ty[4] = { tp.y0, tp.y0, tp.y0 + 1, tp.y0 + 1 };
                         const int tx[4] = { tp.x0, tp.x0 + 1, tp.x0, tp.x0 + 1 };
                         for (int k = 0; k < 4; ++k) if (tp.ok[k]) {
-                            gmy[(size_t)ty[k] * W + tx[k]] += dt * tp.w[k] * gpy;
-                            gmx[(size_t)ty[k] * W + tx[k]] += dt * tp.w[k] * gpx;
+                            amy[(size_t)ty[k] * W + tx[k]] += (ACC)(REAL)(dt * tp.w[k] * gpy);
+                            amx[(size_t)ty[k] * W + tx[k]] += (ACC)(REAL)(dt * tp.w[k] * gpx);
                         }
                     }
                 }
+                for (size_t i = 0; i < HW; ++i) { gmx[i] = (REAL)amx[i]; gmy[i] = (REAL)amy[i]; }
+                free(amx);
             }
         }
     }
     *loss_out = (REAL)loss_total;
 
     for (int k = 0; k < 2; ++k) { free(ny[k]); free(nx[k]); free(alive[k]); if (gst[k]) free(gst[k]); }
-    free(img); free(dimg); free(nnz);
+    free(img); free(aimg); free(adimg); free(nnz);
     FN(evset_free)(&sets[0]); FN(evset_free)(&sets[1]);
     return 0;
 }
@@ -569,7 +573,8 @@ int FN(orc_linear)(const orc_cfg *c,
         evy[k] = (REAL *)malloc(sizeof(REAL) * n); evx[k] = (REAL *)malloc(sizeof(REAL) * n);
     }
     const size_t img_sz = (size_t)B * nslots * 4 * HW;
-    REAL *img = (REAL *)malloc(sizeof(REAL) * img_sz), *dimg = (REAL *)malloc(sizeof(REAL) * img_sz);
+    REAL *img = (REAL *)malloc(sizeof(REAL) * img_sz);
+    ACC *aimg = (ACC *)malloc(sizeof(ACC) * img_sz), *adimg = (ACC *)malloc(sizeof(ACC) * img_sz);
     REAL *gv = gflow ? (REAL *)malloc(sizeof(REAL) * 2 * (size_t)(sets[0].E > 0 ? sets[0].E : 1)) : NULL;
     double loss_total = 0.0;
 
@@ -589,8 +594,8 @@ int FN(orc_linear)(const orc_cfg *c,
             const orc_slot *sl = &slots[q];
             for (int k = 0; k < 2; ++k) {
                 const FN(evset) *s = &sets[k];
-                REAL *im = (k == 0 ? img : dimg) + ((size_t)b * nslots + q) * 4 * HW;
-                memset(im, 0, sizeof(REAL) * 4 * HW);
+                ACC *im = (k == 0 ? aimg : adimg) + ((size_t)b * nslots + q) * 4 * HW;
+                memset(im, 0, sizeof(ACC) * 4 * HW);
                 for (int corner = 0; corner < 4; ++corner)
                     for (int t = sl->lo; t < sl->hi; ++t) for (int i = 0; i < s->n[t]; ++i) {
                         long e = s->off[t] + (long)b * s->n[t] + i;
@@ -600,13 +605,13 @@ int FN(orc_linear)(const orc_cfg *c,
                         FN(corners_t) cr; FN(corners)(py, px, H, W, &cr);
                         REAL nts = (REAL)1 - R_FABS((REAL)sl->tref - s->ts[e]) / (REAL)sl->delta;
                         REAL w = cr.w[corner], wt = w * nts; long pxl = cr.pix[corner];
-                        im[0 * HW + pxl] += w * mp; im[1 * HW + pxl] += w * mn;
-                        im[2 * HW + pxl] += wt * mp; im[3 * HW + pxl] += wt * mn;
+                        im[0 * HW + pxl] += (ACC)(REAL)(w * mp); im[1 * HW + pxl] += (ACC)(REAL)(w * mn);
+                        im[2 * HW + pxl] += (ACC)(REAL)(wt * mp); im[3 * HW + pxl] += (ACC)(REAL)(wt * mn);
                     }
             }
             REAL *im = img + ((size_t)b * nslots + q) * 4 * HW;
-            const REAL *di = dimg + ((size_t)b * nslots + q) * 4 * HW;
-            for (size_t i = 0; i < 4 * HW; ++i) im[i] = im[i] + di[i];
+            const ACC *ai = aimg + ((size_t)b * nslots + q) * 4 * HW, *di = adimg + ((size_t)b * nslots + q) * 4 * HW;
+            for (size_t i = 0; i < 4 * HW; ++i) im[i] = (REAL)(ai[i] + di[i]);       /* loss/flow.py:725-726 */
         }
         if (iwe_out)
             memcpy(iwe_out + (size_t)f * B * nslots * 4 * HW, img, sizeof(REAL) * img_sz);
@@ -670,6 +675,7 @@ int FN(orc_linear)(const orc_cfg *c,
             for (int p = 0; p < P; ++p) for (int b = 0; b < B; ++b) {
                 const REAL *mx = maps + ((size_t)p * B + b) * 2 * HW, *my = mx + HW;
                 REAL *gmx = gf + ((size_t)p * B + b) * 2 * HW, *gmy = gmx + HW;
+                ACC *amx = (ACC *)calloc(2 * HW, sizeof(ACC)), *amy = amx + HW;
                 for (int i = 0; i < s->n[p]; ++i) {
                     long e = s->off[p] + (long)b * s->n[p] + i;
                     if (gv[e * 2] == (REAL)0 && gv[e * 2 + 1] == (REAL)0) continue;
@@ -677,16 +683,18 @@ int FN(orc_linear)(const orc_cfg *c,
                     const int ty[4] = { tp.y0, tp.y0, tp.y0 + 1, tp.y0 + 1 };
                     const int tx[4] = { tp.x0, tp.x0 + 1, tp.x0, tp.x0 + 1 };
                     for (int k = 0; k < 4; ++k) if (tp.ok[k]) {
-                        gmy[(size_t)ty[k] * W + tx[k]] += tp.w[k] * gv[e * 2];
-                        gmx[(size_t)ty[k] * W + tx[k]] += tp.w[k] * gv[e * 2 + 1];
+                        amy[(size_t)ty[k] * W + tx[k]] += (ACC)(REAL)(tp.w[k] * gv[e * 2]);
+                        amx[(size_t)ty[k] * W + tx[k]] += (ACC)(REAL)(tp.w[k] * gv[e * 2 + 1]);
                     }
                 }
+                for (size_t i = 0; i < HW; ++i) { gmx[i] = (REAL)amx[i]; gmy[i] = (REAL)amy[i]; }
+                free(amx);
             }
         }
     }
     *loss_out = (REAL)loss_total;
     for (int k = 0; k < 2; ++k) { free(evy[k]); free(evx[k]); }
-    free(img); free(dimg); if (gv) free(gv);
+    free(img); free(aimg); free(adimg); if (gv) free(gv);
     FN(evset_free)(&sets[0]); FN(evset_free)(&sets[1]);
     return 0;
 }

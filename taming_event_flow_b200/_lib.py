@@ -29,6 +29,11 @@ class TefError(RuntimeError):
     pass
 
 
+class TefShapeError(ValueError, RuntimeError):
+    """A tensor handed to the host mirror has the wrong shape.  The reference fails with a torch RuntimeError (a broadcasting
+    or indexing error somewhere inside the loss); this one is caught as either."""
+
+
 class EmptyWindowError(RuntimeError, ValueError):
     """A temporal scale has no window to concatenate.  The reference fails in ``torch.cat([])`` (loss/flow.py:689), which
     raises RuntimeError up to torch 2.x and ValueError in recent releases (2.11 here): this one is caught by either."""
@@ -79,6 +84,9 @@ class UpdateDesc(ctypes.Structure):
             ("sort_bins", ctypes.c_void_p),
             ("hist", ctypes.c_int),
             ("zero_bins", ctypes.c_int),
+            ("strided", ctypes.c_int * 2),
+            ("ev_strides", (ctypes.c_long * 3) * 2),
+            ("mk_strides", (ctypes.c_long * 3) * 2),
         ]
     )
 

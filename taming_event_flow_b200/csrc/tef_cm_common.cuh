@@ -331,6 +331,29 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
 #ifndef TEF_MERGE_ROUNDS
 #define TEF_MERGE_ROUNDS 1
 #endif
+#ifndef TEF_MERGE_MODE
+#define TEF_MERGE_MODE 0        // 0: runs of neighbouring lanes (the shipped kernels); 1: every lane with the same key (__match_any_sync), experiment
+#endif
+#if TEF_MERGE_MODE == 1
+// Experiment (DESIGN.md decision 14): merge ALL lanes of the warp that reduce into the same slot, neighbours or not.  The lowest
+// lane of every group of equal keys collects its followers one per round (as many rounds as the largest group has followers).
+template <int NV>
+__device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned lane, float (&v)[NV]) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const unsigned leader = (unsigned)__ffs((int)peers) - 1u;
+    unsigned rest = (lane == leader) ? (peers & (peers - 1u)) : 0u;        // the leader's followers, lowest lane first
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+        const unsigned src = rest ? (unsigned)__ffs((int)rest) - 1u : lane;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float n = __shfl_sync(0xffffffffu, v[k], src);
+            if (rest) v[k] += n;
+        }
+        rest &= rest - 1u;
+    }
+    return lane != leader;
+}
+#else
 template <int NV>
 __device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned lane, float (&v)[NV]) {
     const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -355,6 +378,7 @@ __device__ __forceinline__ bool merge_equal_neighbours(unsigned key, unsigned la
     }
     return gave;
 }
+#endif
 
 // splat<true, false> for the events of a whole warp with one-hot {0,1} polarity masks -- the only kind the reference's loader
 // produces (dataloader/base.py:264-278) -- on packed fp32x2 arithmetic, for positions (x, y) that satisfy inside(), with equal

@@ -27,17 +27,31 @@ struct StageTwo {
     float4 *ev_io[2]; const float2 *mk_in[2]; float4 *ev_out[2]; float2 *mk_out[2];
     long rows[2]; float pass_index[2]; const float *ts_override[2]; int nb0;
     int *bins; int first_bin[2]; int n[2]; int tiles_x, tiles, H, W;
+    // element strides (sample, row, column) of the caller's event / mask tensors; strided[k] = 0: contiguous [B][n][4] / [B][n][2]
+    // rows (one 16-byte / 8-byte access).  The reference's custom_collate hands out transposed views of [B][C][n] storage
+    // (dataloader/base.py:414-431), which stay strided after .to(device).
+    int strided[2]; long es[2][3], ms[2][3];
 };
 __device__ __forceinline__ void stage_two_body(const StageTwo &s, int blk) {
     const int k = blk >= s.nb0 ? 1 : 0;
     const long i = (long)(blk - (k ? s.nb0 : 0)) * kThreads + threadIdx.x;
     if (i >= s.rows[k]) return;
-    float4 e = s.ev_io[k][i];
-    e.x = e.x + s.pass_index[k];
-    s.ev_io[k][i] = e;
+    float4 e; float2 m;
+    if (!s.strided[k]) {
+        e = s.ev_io[k][i];
+        e.x = e.x + s.pass_index[k];
+        s.ev_io[k][i] = e;
+        m = s.mk_in[k][i];
+    } else {
+        const long b = i / s.n[k], r = i - b * s.n[k];
+        float *pe = reinterpret_cast<float *>(s.ev_io[k]) + b * s.es[k][0] + r * s.es[k][1];
+        const float *pm = reinterpret_cast<const float *>(s.mk_in[k]) + b * s.ms[k][0] + r * s.ms[k][1];
+        e = make_float4(pe[0] + s.pass_index[k], pe[s.es[k][2]], pe[2 * s.es[k][2]], pe[3 * s.es[k][2]]);
+        pe[0] = e.x;                        // only the timestamp column changes (:457)
+        m = make_float2(pm[0], pm[s.ms[k][2]]);
+    }
     if (s.ts_override[k]) e.x = __ldg(s.ts_override[k]);
     s.ev_out[k][i] = e;
-    const float2 m = s.mk_in[k][i];
     s.mk_out[k][i] = m;
     if (s.bins && !(m.x == 0.0f && m.y == 0.0f))
         atomicAdd(s.bins + sort_bin(s.first_bin[k], s.tiles_x, s.tiles, s.H, s.W, (int)(i / s.n[k]), e.y, e.z), 1);
@@ -151,6 +165,13 @@ extern "C" int tef_update_pass(const tef_update_desc *u, void *stream) {
         s.ev_io[i] = (float4 *)u->events[i]; s.mk_in[i] = (const float2 *)u->masks[i];
         s.ev_out[i] = (float4 *)u->ev_out[i]; s.mk_out[i] = (float2 *)u->mk_out[i];
         s.rows[i] = u->rows[i]; s.pass_index[i] = u->pass_index[i]; s.ts_override[i] = u->ts_override[i];
+        s.strided[i] = u->strided[i] ? 1 : 0;
+        s.n[i] = 1;
+        if (s.strided[i]) {
+            if (u->B < 1 || u->rows[i] % u->B) return TEF_EINVAL;
+            s.n[i] = (int)(u->rows[i] / u->B) > 0 ? (int)(u->rows[i] / u->B) : 1;
+            for (int j = 0; j < 3; ++j) { s.es[i][j] = u->ev_strides[i][j]; s.ms[i][j] = u->mk_strides[i][j]; }
+        }
     }
     s.bins = nullptr;
     if (u->hist) {

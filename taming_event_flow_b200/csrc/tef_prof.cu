@@ -1,5 +1,6 @@
 #include "tef_prof.cuh"
 #include "../../include/tef_b200.h"
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -11,39 +12,48 @@ static const char *kNames[K_COUNT] = {
     "encoding_kernels", "microbench_kernels", "loader_kernels", "validation_kernels", "smoothing_kernels"
 };
 
-struct Pair { cudaEvent_t a, b; int id; };
-static std::mutex g_mu;
-static bool g_on = false;
-static long g_launches[K_COUNT] = {0};
+struct Pair { cudaEvent_t a, b; int id, dev; };
+constexpr int kMaxDev = 64;
+static std::mutex g_mu;                               // guards the pools, the pending list and the timing totals
+static std::atomic<bool> g_on{false};
+static std::atomic<long> g_launches[K_COUNT];
 static double g_ms[K_COUNT] = {0};
 static long g_timed[K_COUNT] = {0};
 static std::vector<Pair> g_pending;
-static std::vector<Pair> g_free;
+static std::vector<Pair> g_free[kMaxDev];             // events belong to the device they were created on
 
-ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(-1) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    ++g_launches[id];
-    if (!g_on) return;
-    Pair p;
-    if (!g_free.empty()) { p = g_free.back(); g_free.pop_back(); }
-    else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
-    p.id = id;
-    cudaEventRecord(p.a, st);
-    g_pending.push_back(p);
-    slot = (int)g_pending.size() - 1;
+ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), a(nullptr), b(nullptr), dev(-1) {
+    g_launches[id].fetch_add(1, std::memory_order_relaxed);
+    if (!g_on.load(std::memory_order_acquire)) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;   // no timing inside a graph capture
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDev) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_free[d].empty()) { a = g_free[d].back().a; b = g_free[d].back().b; g_free[d].pop_back(); }
+    }
+    if (!a && (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess)) { a = b = nullptr; return; }
+    dev = d;
+    cudaEventRecord(a, st);
 }
 ProfScope::~ProfScope() {
-    if (slot < 0) return;
+    if (dev < 0) return;
+    cudaEventRecord(b, st);
     std::lock_guard<std::mutex> lk(g_mu);
-    cudaEventRecord(g_pending[slot].b, st);
+    g_pending.push_back(Pair{a, b, id, dev});
 }
 
-static void drain() {
+static void drain() {                                 // caller holds g_mu
+    int cur = 0;
+    cudaGetDevice(&cur);
     for (auto &p : g_pending) {
+        if (p.dev != cur) cudaSetDevice(p.dev);
         cudaEventSynchronize(p.b);
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { g_ms[p.id] += ms; ++g_timed[p.id]; }
-        g_free.push_back(p);
+        g_free[p.dev].push_back(p);
+        if (p.dev != cur) cudaSetDevice(cur);
     }
     g_pending.clear();
 }
@@ -54,16 +64,16 @@ using namespace tef;
 
 extern "C" void tef_prof_enable(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!on) drain();
-    if (on && g_free.size() < 2048) {               // create the event pool outside any timed region
-        while (g_free.size() < 2048) { Pair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.id = 0; g_free.push_back(p); }
-    }
-    g_on = on != 0;
+    if (!on) { g_on.store(false, std::memory_order_release); drain(); return; }
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDev)        // create the event pool outside any timed region
+        while (g_free[d].size() < 2048) { Pair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.id = 0; p.dev = d; g_free[d].push_back(p); }
+    g_on.store(true, std::memory_order_release);
 }
 extern "C" void tef_prof_reset(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     drain();
-    for (int i = 0; i < K_COUNT; ++i) { g_launches[i] = 0; g_ms[i] = 0; g_timed[i] = 0; }
+    for (int i = 0; i < K_COUNT; ++i) { g_launches[i].store(0); g_ms[i] = 0; g_timed[i] = 0; }
 }
 extern "C" int tef_prof_num_kernels(void) { return K_COUNT; }
 extern "C" const char *tef_prof_name(int id) { return (id >= 0 && id < K_COUNT) ? kNames[id] : ""; }
@@ -73,12 +83,11 @@ extern "C" int tef_prof_read(int id, double *ms_total, long *timed_launches, lon
     drain();
     if (ms_total) *ms_total = g_ms[id];
     if (timed_launches) *timed_launches = g_timed[id];
-    if (launches) *launches = g_launches[id];
+    if (launches) *launches = g_launches[id].load();
     return 0;
 }
 extern "C" long tef_launch_count(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
     long n = 0;
-    for (int i = 0; i < K_COUNT; ++i) n += g_launches[i];
+    for (int i = 0; i < K_COUNT; ++i) n += g_launches[i].load(std::memory_order_relaxed);
     return n;
 }

@@ -12,10 +12,15 @@ enum KernelId {
     K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER, K_LIN_FWD, K_LIN_BWD, K_PRIMITIVE, K_ENCODING, K_MICROBENCH, K_LOADER, K_VALIDATION, K_SMOOTH, K_COUNT
 };
 
+// The event pair lives in the scope itself and joins the pending list only in the destructor, so a concurrent
+// tef_prof_read / tef_prof_reset (the autograd backward runs on a worker thread) can never invalidate it.  With timing
+// off a scope costs one relaxed atomic increment: no lock on the launch path.
 struct ProfScope {
-    int id; cudaStream_t st; int slot;
+    int id; cudaStream_t st; cudaEvent_t a, b; int dev;     // dev < 0: not timed
     ProfScope(int id, cudaStream_t st);
     ~ProfScope();
+    ProfScope(const ProfScope &) = delete;
+    ProfScope &operator=(const ProfScope &) = delete;
 };
 
 }  // namespace tef

@@ -12,22 +12,40 @@ from .._lib import check, lib, ptr, require_cuda, stream
 
 _l = ctypes.c_long
 
+# Upstream's ``index_put_`` raises IndexError for an event outside the sensor (dataloader/encodings.py:23-27).  Mirroring that
+# needs the kernel's out-of-bounds flag on the host, i.e. one 4-byte read-back (a stream synchronisation) per call.  Set to
+# False to skip the read-back: such events are then dropped silently.
+CHECK_BOUNDS = True
+
 
 def _prep(*ts):
     require_cuda(*ts)
     return [t.contiguous().float() for t in ts]
 
 
+def _oob_flag(device):
+    return torch.zeros((1,), dtype=torch.int32, device=device) if CHECK_BOUNDS else None
+
+
+def _raise_if_oob(flag, sensor_size):
+    if flag is not None and int(flag.item()) != 0:
+        raise IndexError("event coordinates out of bounds for a sensor of size %s (upstream: index_put_ raises IndexError)" % (tuple(sensor_size),))
+
+
 def events_to_image(xs, ys, ps, sensor_size=(180, 240), accumulate=True):
     """Accumulate events into an image (upstream ``dataloader/encodings.py:8-29``).
 
-    Coordinates are truncated like ``.long()``; negative ones wrap like Python indexing.  Events beyond the
-    sensor (where upstream raises ``IndexError``) are dropped.
+    Coordinates are truncated like ``.long()``; negative ones wrap like Python indexing; events beyond the sensor raise
+    ``IndexError`` like upstream (see `CHECK_BOUNDS`).  ``accumulate=False`` keeps the last event of every pixel, the result of
+    upstream's CPU ``index_put_`` (deterministic here: highest event index per pixel).
     """
     xs, ys, ps = _prep(xs, ys, ps)
     H, W = int(sensor_size[0]), int(sensor_size[1])
     img = torch.empty((H, W), dtype=torch.float32, device=xs.device)
-    check(lib().tef_events_to_image(ptr(xs), ptr(ys), ptr(ps), ptr(img), _l(xs.numel()), H, W, int(bool(accumulate)), stream()), "tef_events_to_image")
+    oob = _oob_flag(xs.device)
+    check(lib().tef_events_to_image(ptr(xs), ptr(ys), ptr(ps), ptr(img), _l(xs.numel()), H, W, int(bool(accumulate)), ptr(oob), stream()),
+          "tef_events_to_image")
+    _raise_if_oob(oob, sensor_size)
     return img
 
 
@@ -37,7 +55,10 @@ def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
     xs, ys, ts, ps = _prep(xs, ys, ts, ps)
     H, W = int(sensor_size[0]), int(sensor_size[1])
     out = torch.empty((int(num_bins), H, W), dtype=torch.float32, device=xs.device)
-    check(lib().tef_events_to_voxel(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(out), _l(xs.numel()), int(num_bins), H, W, stream()), "tef_events_to_voxel")
+    oob = _oob_flag(xs.device)
+    check(lib().tef_events_to_voxel(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(out), _l(xs.numel()), int(num_bins), H, W, ptr(oob), stream()),
+          "tef_events_to_voxel")
+    _raise_if_oob(oob, sensor_size)
     return out
 
 
@@ -47,7 +68,9 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
     xs, ys, ps = _prep(xs, ys, ps)
     H, W = int(sensor_size[0]), int(sensor_size[1])
     out = torch.empty((2, H, W), dtype=torch.float32, device=xs.device)
-    check(lib().tef_events_to_channels(ptr(xs), ptr(ys), ptr(ps), ptr(out), _l(xs.numel()), H, W, stream()), "tef_events_to_channels")
+    oob = _oob_flag(xs.device)
+    check(lib().tef_events_to_channels(ptr(xs), ptr(ys), ptr(ps), ptr(out), _l(xs.numel()), H, W, ptr(oob), stream()), "tef_events_to_channels")
+    _raise_if_oob(oob, sensor_size)
     return out
 
 

@@ -16,7 +16,7 @@ import os
 import torch
 
 from .. import _lib
-from .._lib import CmDesc, check, lib, ptr, require_cuda, stream
+from .._lib import CmDesc, TefShapeError, check, lib, ptr, require_cuda, stream
 
 _MODES = {"one": 1, "two": 2, "four": 4}
 
@@ -204,11 +204,15 @@ class BaseEventWarping(torch.nn.Module):
         if F > _lib.MAX_FLOWS:
             raise _lib.TefError("at most %d flow maps per pass" % _lib.MAX_FLOWS)
         f0 = flow_list[0]
-        if not f0.is_cuda or f0.device.index != torch.cuda.current_device():
-            require_cuda(f0)
-        B, C, H, W = f0.shape
+        require_cuda(*flow_list)
+        B, C, H, W = f0.shape if f0.dim() == 4 else (0, 0, 0, 0)
         if C != 2 or H != self.res[0] or W != self.res[1]:
-            raise ValueError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(f0.shape)))
+            raise TefShapeError("flow maps must be [B,2,%d,%d], got %s" % (self.res[0], self.res[1], tuple(f0.shape)))
+        for fl in flow_list[1:]:
+            if fl.shape != f0.shape:       # every map is read as [B,2,H,W] with the batch size of the first one
+                raise TefShapeError("every flow map of a pass must be %s, got %s" % (tuple(f0.shape), tuple(fl.shape)))
+        if w.shape is not None and w.shape != (F, B, H, W):
+            raise TefShapeError("flow maps changed shape inside a loss window: %s, then %s" % (w.shape, (F, B, H, W)))
         if w.packed is None:
             w.shape = (F, B, H, W)
             Wp = (W + 3) & ~1                      # dual-phase, zero-padded maps (csrc/tef_device.cuh)
@@ -235,10 +239,15 @@ class BaseEventWarping(torch.nn.Module):
         round_ts = self.config["loss"]["round_ts"]
         dev = w.packed.device
         for k, (ev, mk) in enumerate(((event_list, pol_mask), (d_event_list, d_pol_mask))):
-            if not (ev.is_cuda and mk.is_cuda):
-                require_cuda(ev, mk)
-            Bk, N = ev.shape[0], ev.shape[1]
-            rows = Bk * N
+            require_cuda(ev, mk)
+            # the kernels read B * N rows of 4 (events) and 2 (mask) floats, with B taken from the flow maps: anything else
+            # would be an out-of-bounds device read, where upstream fails with a torch shape error
+            if ev.dim() != 3 or ev.shape[0] != B or ev.shape[2] != 4:
+                raise TefShapeError("event list must be [%d,N,4] (batch size of the flow maps), got %s" % (B, tuple(ev.shape)))
+            if mk.dim() != 3 or mk.shape[0] != B or mk.shape[1] != ev.shape[1] or mk.shape[2] != 2:
+                raise TefShapeError("polarity mask must be [%d,%d,2] like its event list, got %s" % (B, ev.shape[1], tuple(mk.shape)))
+            N = ev.shape[1]
+            rows = B * N
             buf = w.ws.get(("stage", k, t), (rows, 6), torch.float32, dev)
             base = buf.data_ptr()
             w.ev[k].append(base)
@@ -252,17 +261,22 @@ class BaseEventWarping(torch.nn.Module):
                 u.ts_override[k] = ov.data_ptr()
             if rows == 0:
                 continue
-            if ev.is_contiguous() and ev.dtype == torch.float32:
-                u.events[k], u.pass_index[k] = ev.data_ptr(), float(t)
+            if ev.dtype != torch.float32:
+                ev[:, :, 0:1] += t             # the in-place update of the caller's tensor, then a float copy for the kernels
+                ev = ev.float()
+                keep.append(ev)
+                u.pass_index[k] = 0.0
             else:
-                ev[:, :, 0:1] += t
-                src = ev.contiguous().float()
-                keep.append(src)
-                u.events[k], u.pass_index[k] = src.data_ptr(), 0.0
-            if not (mk.is_contiguous() and mk.dtype == torch.float32):
-                mk = mk.contiguous().float()
+                u.pass_index[k] = float(t)
+            if mk.dtype != torch.float32:
+                mk = mk.float()
                 keep.append(mk)
-            u.masks[k] = mk.data_ptr()
+            u.events[k], u.masks[k] = ev.data_ptr(), mk.data_ptr()
+            if not (ev.is_contiguous() and mk.is_contiguous()):
+                # e.g. the transposed views upstream's custom_collate returns: read through their strides (same launch)
+                u.strided[k] = 1
+                for j in range(3):
+                    u.ev_strides[k][j], u.mk_strides[k][j] = ev.stride(j), mk.stride(j)
             u.ev_out[k], u.mk_out[k] = base, base + rows * 16
         if t >= P:
             # passes beyond the loss window are not part of the loss (upstream never reads them); only the in-place
@@ -415,6 +429,10 @@ class BaseEventWarping(torch.nn.Module):
         w = self._win
         if w.packed is None:
             raise IndexError("no flow maps: call update() first")
+        if self._passes > self._max_passes():
+            # upstream's priors cover every pass given to update(); here only the passes of the loss window are packed
+            raise NotImplementedError("the smoothness priors cover at most passes_loss = %d passes per window, update() was called %d times; "
+                                      "call reset() after every loss like upstream's train_flow.py:136-137" % (self._max_passes(), self._passes))
         flat = [fl for per_pass in w.flows for fl in per_pass]
         return _Smoothness.apply(self, w, temporal, self._passes, *flat).sum()
 

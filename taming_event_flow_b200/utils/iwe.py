@@ -10,7 +10,7 @@ import ctypes
 
 import torch
 
-from .._lib import check, lib, ptr, require_cuda, stream
+from .._lib import TefShapeError, check, lib, ptr, require_cuda, stream
 
 _f = ctypes.c_float
 _l = ctypes.c_long
@@ -131,8 +131,13 @@ class _Purge(torch.autograd.Function):
 def purge_unfeasible(event_loc, event_pol_mask, res):
     """Zero the location and polarity mask of events warped outside the image (upstream ``utils/iwe.py:43-60``)."""
     require_cuda(event_loc, event_pol_mask)
-    cols = event_pol_mask.shape[-1]
+    if event_loc.dim() < 1 or event_loc.shape[-1] != 2:
+        raise TefShapeError("event_loc must be [..., 2] (y, x), got %s" % (tuple(event_loc.shape),))
+    cols = event_pol_mask.shape[-1] if event_pol_mask.dim() else 0
     if event_pol_mask.shape != event_loc.shape:       # e.g. a [B,N,1] mask (loss/flow_val.py:58): broadcast like upstream
+        if event_pol_mask.dim() != event_loc.dim() or event_pol_mask.shape[:-1] != event_loc.shape[:-1] or cols not in (1, 2):
+            raise TefShapeError("polarity mask %s does not match event locations %s ([..., 1] or [..., 2] expected)"
+                                % (tuple(event_pol_mask.shape), tuple(event_loc.shape)))
         event_pol_mask = event_pol_mask.expand_as(event_loc)
     loc, mask = _Purge.apply(event_loc, event_pol_mask, int(res[0]), int(res[1]))
     return loc, (mask if cols == mask.shape[-1] else mask[..., 0:cols])
@@ -210,12 +215,22 @@ def interpolate(idx, weights, res, polarity_mask=None, zeros=None):
     """Accumulate weighted events into an image of warped events (upstream ``utils/iwe.py:116-136``).
 
     :return: [batch_size x 1 x H x W] image; ``zeros`` (if given) is the start image and is not modified
+
+    Indices outside ``[0, H*W)`` (which `get_interpolation` never produces; upstream's ``scatter_add_`` raises on them)
+    are skipped.
     """
     require_cuda(idx, weights, polarity_mask, zeros)
     return _Interpolate.apply(idx, weights, polarity_mask, zeros, int(res[0]), int(res[1]))
 
 
 # --------------------------------------------------------------------------------------------
+def _check_deblur_shapes(fl, ev, H, W):
+    if ev.dim() != 3 or ev.shape[2] != 4:
+        raise TefShapeError("event_list must be [B,N,4], got %s" % (tuple(ev.shape),))
+    if tuple(fl.shape) != (ev.shape[0], 2, H, W):
+        raise TefShapeError("flow must be [%d,2,%d,%d], got %s" % (ev.shape[0], H, W, tuple(fl.shape)))
+
+
 def _deblur_into(out_view, batch_stride, flow, event_list, res, round_idx, pol, pol_stride, round_flow):
     B, N = event_list.shape[0], event_list.shape[1]
     check(lib().tef_deblur_events(ptr(flow), ptr(event_list), ptr(pol) if pol is not None else None, _l(pol_stride), ptr(out_view), _l(batch_stride),
@@ -230,9 +245,13 @@ def deblur_events(flow, event_list, res, round_idx=True, polarity_mask=None, rou
     require_cuda(flow, event_list, polarity_mask)
     H, W = int(res[0]), int(res[1])
     fl, ev = _c(flow.detach()), _c(event_list.detach())
+    _check_deblur_shapes(fl, ev, H, W)
     B = ev.shape[0]
     # upstream multiplies the weights by the polarity mask in both branches (:216-222)
     pol = _c(polarity_mask.detach()) if polarity_mask is not None else None
+    if pol is not None and tuple(pol.shape) != (B, ev.shape[1], 1):
+        # the kernel reads one mask value per event (stride 1): a [B,N,2] mask would be read with the wrong stride
+        raise TefShapeError("polarity_mask must be [%d,%d,1] (one column of the loader's mask), got %s" % (B, ev.shape[1], tuple(pol.shape)))
     iwe = torch.empty((B, 1, H, W), dtype=torch.float32, device=ev.device)
     _deblur_into(iwe, H * W, fl, ev, res, round_idx, pol, 1, round_flow)
     return iwe
@@ -243,7 +262,10 @@ def compute_pol_iwe(flow, event_list, res, pol_mask, round_idx=True, round_flow=
     require_cuda(flow, event_list, pol_mask)
     H, W = int(res[0]), int(res[1])
     fl, ev, pm = _c(flow.detach()), _c(event_list.detach()), _c(pol_mask.detach())
+    _check_deblur_shapes(fl, ev, H, W)
     B = ev.shape[0]
+    if tuple(pm.shape) != (B, ev.shape[1], 2):
+        raise TefShapeError("pol_mask must be [%d,%d,2], got %s" % (B, ev.shape[1], tuple(pm.shape)))
     iwe = torch.empty((B, 2, H, W), dtype=torch.float32, device=ev.device)
     for ch in range(2):
         _deblur_into(iwe[:, ch], 2 * H * W, fl, ev, res, round_idx, pm.view(-1)[ch:], 2, round_flow)

@@ -191,3 +191,97 @@ def test_get_hot_event_mask_against_its_specification():
         em, er = orc.get_hot_event_mask(rate.numpy(), idx, max_px=max_px)
         assert np.array_equal(m.cpu().numpy(), em) and np.array_equal(r.cpu().numpy(), er)
         assert int((m == 0).sum()) == (0 if idx <= 5 else min(max_px, 150))
+
+
+def test_encodings_out_of_range_raises_like_index_put():
+    """An event outside the sensor: the reference's index_put_ raises IndexError (dataloader/encodings.py:23-27; checked live in
+    tests/test_primitives_vs_reference_live.py).  Negative coordinates down to -size wrap like Python indexing."""
+    from taming_event_flow_b200.dataloader import encodings as enc
+
+    H, W = 12, 20
+    xs = torch.tensor([3.0, 19.0, -1.0, 5.7]).cuda()
+    ys = torch.tensor([2.0, 11.0, -12.0, 0.2]).cuda()
+    ts = torch.tensor([0.0, 0.3, 0.6, 1.0]).cuda()
+    ps = torch.tensor([1.0, -1.0, 1.0, -1.0]).cuda()
+    img = enc.events_to_image(xs, ys, ps, (H, W)).cpu().numpy()
+    ref = orc.events_to_image(xs.cpu().numpy(), ys.cpu().numpy(), ps.cpu().numpy(), (H, W))
+    assert np.array_equal(img, ref) and img[0, 19] == 1.0 and img[0, 5] == -1.0       # (-12, -1) wraps to (0, 19); (0.2, 5.7) truncates
+    for bad_x, bad_y in ((20.0, 0.0), (0.0, 12.0), (-21.0, 0.0), (0.0, -13.0), (1e9, 0.0)):
+        bx, by = xs.clone(), ys.clone()
+        bx[1], by[1] = bad_x, bad_y
+        with pytest.raises(IndexError):
+            enc.events_to_image(bx, by, ps, (H, W))
+        with pytest.raises(IndexError):
+            enc.events_to_image(bx, by, ps, (H, W), accumulate=False)
+        with pytest.raises(IndexError):
+            enc.events_to_channels(bx, by, ps, (H, W))
+        with pytest.raises(IndexError):
+            enc.events_to_voxel(bx, by, ts, ps, 3, (H, W))
+    enc.CHECK_BOUNDS = False                     # no read-back: the event is dropped
+    try:
+        bx = xs.clone()
+        bx[1] = 20.0
+        ch = enc.events_to_channels(bx, ys, ps, (H, W))
+        assert ch.sum().item() == 3.0
+    finally:
+        enc.CHECK_BOUNDS = True
+
+
+@pytest.mark.parametrize("n,offset", [(1, 0), (3, 1), (4, 0), (1001, 1), (1002, 2), (4096, 0), (50001, 3)])
+def test_encodings_vector_loads_tails_and_unaligned_views(n, offset):
+    """Four events per thread with 16-byte loads: counts that are not multiples of four and views that start at an
+    unaligned element take the element-wise path; same results bit for bit."""
+    from taming_event_flow_b200.dataloader.encodings import events_to_channels, events_to_image, events_to_voxel
+
+    H, W, bins = 40, 56, 5
+    g = torch.Generator().manual_seed(n * 7 + offset)
+    xs = torch.randint(0, W, (n + offset,), generator=g).float()
+    ys = torch.randint(0, H, (n + offset,), generator=g).float()
+    ts = torch.rand(n + offset, generator=g)
+    ps = (torch.randint(0, 2, (n + offset,), generator=g) * 2 - 1).float()
+    cx, cy, ct, cp = (a.cuda()[offset:] for a in (xs, ys, ts, ps))
+    hx, hy, ht, hp = (a[offset:].numpy() for a in (xs, ys, ts, ps))
+    assert np.array_equal(events_to_channels(cx, cy, cp, (H, W)).cpu().numpy(), orc.events_to_channels(hx, hy, hp, (H, W)))
+    assert np.array_equal(events_to_image(cx, cy, cp, (H, W)).cpu().numpy(), orc.events_to_image(hx, hy, hp, (H, W)))
+    v = events_to_voxel(cx, cy, ct, cp, bins, (H, W)).cpu().numpy()
+    assert rel_err(v, orc.events_to_voxel(hx, hy, ht, hp, bins, (H, W)))[0] < TOL
+
+
+@pytest.mark.parametrize("n", [0, 5, 20000])
+def test_events_to_image_without_accumulation_keeps_the_last_event(n):
+    """accumulate=False: index_put_ without accumulation; the reference's CPU kernel applies the events in order, so the last
+    event of a pixel wins.  The GPU result must be that, deterministically (run twice, heavy pixel reuse)."""
+    from taming_event_flow_b200.dataloader.encodings import events_to_image
+
+    H, W = 16, 24
+    g = torch.Generator().manual_seed(n)
+    xs = torch.randint(0, W, (n,), generator=g).float()
+    ys = torch.randint(0, H, (n,), generator=g).float()
+    ps = torch.randn(n, generator=g)
+    ref = np.zeros((H, W), np.float32)
+    for i in range(n):
+        ref[int(ys[i]), int(xs[i])] = ps[i]
+    for _ in range(2):
+        out = events_to_image(xs.cuda(), ys.cuda(), ps.cuda(), (H, W), accumulate=False).cpu().numpy()
+        assert np.array_equal(out, ref)
+
+
+def test_mask_shapes_are_validated():
+    from taming_event_flow_b200._lib import TefShapeError
+    from taming_event_flow_b200.utils.iwe import compute_pol_iwe, deblur_events, purge_unfeasible
+
+    B, N, H, W = 2, 10, 8, 12
+    loc = torch.rand(B, N, 2).cuda() * 6
+    out_l, out_m = purge_unfeasible(loc, torch.ones(B, N, 1).cuda(), (H, W))        # [B,N,1] broadcasts like upstream
+    assert out_m.shape == (B, N, 1)
+    for bad in (torch.ones(B, N - 1, 2), torch.ones(B, N, 3), torch.ones(N, 2)):
+        with pytest.raises(TefShapeError):
+            purge_unfeasible(loc, bad.cuda(), (H, W))
+    flow, ev = torch.zeros(B, 2, H, W).cuda(), torch.zeros(B, N, 4).cuda()
+    deblur_events(flow, ev, (H, W), polarity_mask=torch.ones(B, N, 1).cuda())
+    with pytest.raises(TefShapeError):          # a two-column mask would be read with the wrong stride
+        deblur_events(flow, ev, (H, W), polarity_mask=torch.ones(B, N, 2).cuda())
+    with pytest.raises(TefShapeError):
+        compute_pol_iwe(flow, ev, (H, W), torch.ones(B, N, 1).cuda())
+    with pytest.raises(TefShapeError):
+        deblur_events(torch.zeros(B, 2, H, W + 1).cuda(), ev, (H, W))

@@ -89,3 +89,17 @@ def test_encodings_and_deblur(seed):
         got = orc.compute_pol_iwe(flow, ev, (H, W), pol, round_idx=round_idx, round_flow=True)
         want = ref_iwe.compute_pol_iwe(T(flow), T(ev), (H, W), T(pol), round_idx=round_idx, round_flow=True)
         assert same(want, got), round_idx
+
+
+def test_reference_encoding_error_and_last_writer_behaviour():
+    """What the CUDA encodings mirror (tests/test_primitives_gpu.py): an event outside the sensor raises IndexError in the
+    reference's index_put_ (dataloader/encodings.py:23-27), negative coordinates wrap, and accumulate=False keeps the LAST
+    event of a pixel."""
+    import torch
+
+    _, ref_enc = _ref()
+    for bad_x, bad_y in ((20.0, 0.0), (0.0, 12.0), (-21.0, 0.0), (0.0, -13.0)):
+        with pytest.raises(IndexError):
+            ref_enc.events_to_image(torch.tensor([bad_x]), torch.tensor([bad_y]), torch.tensor([1.0]), sensor_size=(12, 20))
+    img = ref_enc.events_to_image(torch.tensor([-1.0, 3, 3]), torch.tensor([-12.0, 1, 1]), torch.tensor([1.0, 2, 5]), sensor_size=(12, 20), accumulate=False)
+    assert img[0, 19] == 1.0 and img[1, 3] == 5.0
