@@ -74,6 +74,9 @@ VAL_WORKLOADS = {
     "validation_480x640_500kev": dict(N=500_000, H=480, W=640, P=10),
 }
 DEFAULT_WORKLOAD = "iterative_480x640_1Mev"
+# training-step settings (measured on B200): "eager" | "graph", "f32" | "bf16"
+TRAIN_MODE_DEFAULT = "eager"
+TRAIN_DTYPE_DEFAULT = "f32"
 
 
 def fast_sequence(seed, wl, device="cpu", n_override=None):
@@ -603,7 +606,7 @@ def run_train(args, wl, quiet=False):
     from taming_event_flow_b200 import synthetic as syn
     from taming_event_flow_b200.flownet import RecEVFlowNet
     from taming_event_flow_b200.loss import flow as tef_flow
-    from taming_event_flow_b200.training import shard_range, train_step
+    from taming_event_flow_b200.training import GradReducer, GraphedTrainStep, shard_range, train_step
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -625,9 +628,16 @@ def run_train(args, wl, quiet=False):
     cfg = syn.loss_config(wl["H"], wl["W"], B_local, P, wl["S"], wl["mode"], warping=wl["warping"])
     loss_fn = getattr(tef_flow, wl["warping"])(cfg, dev)
     torch.manual_seed(0)
-    # the network stays on PyTorch/cuDNN (north_star); channels_last is the one setting applied to it (1.6x on B200)
+    # The network stays on PyTorch/cuDNN (north_star).  What is applied to it: channels_last, optional bf16
+    # autocast (the CM loss stays fp32), one CUDA graph over forward + loss + backward, a flat gradient buffer with a bucketed
+    # SUM all-reduce issued under the backward pass, fused Adam.
+    mode = getattr(args, "train_mode", None) or os.environ.get("TEF_TRAIN_MODE", TRAIN_MODE_DEFAULT)
+    dtype = getattr(args, "train_dtype", None) or os.environ.get("TEF_TRAIN_DTYPE", TRAIN_DTYPE_DEFAULT)
+    autocast = torch.bfloat16 if dtype == "bf16" else None
+    torch.backends.cudnn.benchmark = True
     model = RecEVFlowNet(num_bins=2).to(dev).to(memory_format=torch.channels_last)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)      # the optimizer step stays outside the captured graph
+    reducer = GradReducer(list(model.parameters()), world)
     from taming_event_flow_b200.dataloader.encodings import events_to_channels_batched
 
     def encode(ev, dv):
@@ -636,11 +646,25 @@ def run_train(args, wl, quiet=False):
 
     nsteps = args.warmup + args.steps
     masks = [(seq["masks"][t].to(dev), seq["d_masks"][t].to(dev)) for t in range(P)]
-    evs = [[(seq["events"][t].to(dev), seq["d_events"][t].to(dev)) for t in range(P)] for _ in range(nsteps)]
+    src = [(seq["events"][t].to(dev), seq["d_events"][t].to(dev)) for t in range(P)]
 
-    def step(i):
-        windows = [(evs[i][t][0], masks[t][0], evs[i][t][1], masks[t][1]) for t in range(P)]
-        return train_step(model, loss_fn, opt, windows, flow_scaling=32.0, clip_grad=100.0, world_size=world, encode=encode)
+    if mode == "graph":
+        # static inputs of the captured step; a step's events are copied in before the replay (inside the timed region)
+        static = [(src[t][0].clone(), masks[t][0], src[t][1].clone(), masks[t][1]) for t in range(P)]
+        graphed = GraphedTrainStep(model, loss_fn, opt, static, flow_scaling=32.0, clip_grad=100.0, encode=encode, reducer=reducer, autocast=autocast)
+
+        def step(i):
+            for t in range(P):
+                static[t][0].copy_(src[t][0])
+                static[t][2].copy_(src[t][1])
+            return graphed.step()
+    else:
+        evs = [[(src[t][0].clone(), src[t][1].clone()) for t in range(P)] for _ in range(nsteps)]
+
+        def step(i):
+            windows = [(evs[i][t][0], masks[t][0], evs[i][t][1], masks[t][1]) for t in range(P)]
+            return train_step(model, loss_fn, opt, windows, flow_scaling=32.0, clip_grad=100.0, world_size=world, encode=encode, reducer=reducer,
+                              autocast=autocast)
 
     def barrier():
         torch.cuda.synchronize()
@@ -664,9 +688,10 @@ def run_train(args, wl, quiet=False):
     ms = float(t.item())
     res = {"metric": "train_throughput", "value": B_global * P * args.steps / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch fp32/TF32 cuDNN, channels_last, 31.4M params)",
-                          optimizer="Adam lr 1e-5, clip 100, SUM all-reduce of gradients"),
+           "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch/cuDNN, channels_last, %s, 31.4M params)" % ("bf16 autocast, fp32 CM loss" if autocast else "fp32/TF32"),
+                          step_mode=("one CUDA graph over forward + CM loss + backward; all-reduce, clip, Adam eager" if mode == "graph" else "eager"),
+                          optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets) under the backward pass" % len(reducer.buckets)),
            "loss": float(loss.item()), "events_per_step": B_global * P * (wl["N"] + wl["Nd"])}
     if own_pg:
         dist.barrier()
@@ -791,6 +816,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-mode", default=None, choices=["eager", "graph"], help="training-step workloads: eager launches or one CUDA graph")
+    ap.add_argument("--train-dtype", default=None, choices=["f32", "bf16"], help="training-step workloads: network compute type (the CM loss is fp32)")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
                     choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + sorted(INFER_WORKLOADS) + sorted(VAL_WORKLOADS))
     args = ap.parse_args()

@@ -74,3 +74,49 @@ def test_sum_allreduce_matches_single_process(tmp_path):
         assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-7)
     assert got["nbytes"] == sum(p.numel() * 4 for p in model.parameters())
     assert got["slow"] == 2.0
+
+
+def _reducer_worker(rank, world, port, gb, out):
+    from taming_event_flow_b200.training import GradReducer
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(123)
+    data = torch.randn(gb, 2, 8, 8)
+    a, b = shard_range(gb, world, rank)
+    model = _model().to(memory_format=torch.channels_last)
+    red = GradReducer(list(model.parameters()), world, bucket_bytes=16)          # several buckets, issued from the grad hooks
+    res = []
+    for step in range(2):                                                        # the second step checks the re-arming
+        red.zero()
+        # a weight-shared "unrolled" loss, like back-propagation through time: every parameter is used twice
+        (_loss(model, data[a:b]) + 0.5 * _loss(model, data[a:b] * (1.0 + step))).backward()
+        launched_in_backward = sum(red._launched)
+        nbytes = red.finish()
+        res.append({"grads": [p.grad.clone() for p in model.parameters()], "nbytes": nbytes, "in_backward": launched_in_backward,
+                    "views": all(p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr() for p in model.parameters()),
+                    "strides": all(p.grad.stride() == p.stride() for p in model.parameters()), "buckets": len(red.buckets)})
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_overlapped_buckets_match_single_process(tmp_path):
+    """GradReducer: flat gradient buffer (views with the parameters' strides), bucketed SUM all-reduce issued from
+    post-accumulate-grad hooks while the backward pass is still running; equals the single-process global batch."""
+    gb, world = 6, 2
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_reducer_worker, args=(world, _free_port(), gb, out), nprocs=world, join=True)
+    got = torch.load(out)
+    torch.manual_seed(123)
+    data = torch.randn(gb, 2, 8, 8)
+    for step, r in enumerate(got):
+        model = _model()
+        (_loss(model, data) + 0.5 * _loss(model, data * (1.0 + step))).backward()
+        for g, p in zip(r["grads"], model.parameters()):
+            assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-7)
+        assert r["nbytes"] == sum(p.numel() * 4 for p in model.parameters())
+        assert r["views"] and r["strides"] and r["buckets"] >= 2
+        assert r["in_backward"] == r["buckets"]            # every bucket was issued from a hook, before backward() returned
