@@ -51,8 +51,9 @@ typedef struct tef_cm_desc {
     int mode;              /* iterative_mode: 1 one, 2 two, 4 four (ignored by Linear) */
     int border_comp;       /* BaseEventWarping.border_compensation                    */
     int loss_scaling;      /* BaseEventWarping.loss_scaling                           */
-    int deterministic;     /* 0: fp32 vector reductions; 1: 64-bit fixed-point (2^-40) integer reductions -- order-independent,
-                              bit-reproducible; img / gflow then hold int64 instead of float (twice the bytes)  */
+    int deterministic;     /* 0: fp32 vector reductions; 1: 64-bit fixed-point integer reductions -- order-independent, bit-reproducible.
+                              img then holds two int64 words per value (high 2^-40, low 2^-88: every fp32 addend exactly; four times
+                              the bytes), gflow one int64 per value at 2^-40 relative to a power-of-two scale (twice the bytes) */
     /* staged events, set 0 = with gradient, set 1 = detached; pass t holds [B][n] rows:
        ev = float4 (ts + t, y, x, p), mk = float2 (pos, neg).  Written by tef_stage_events. */
     const void *ev[2][TEF_MAX_PASSES];
@@ -66,7 +67,8 @@ typedef struct tef_cm_desc {
                               after backward the planes hold (dL/dcount, dL/dtime-weighted) in both phases       */
     double *acc_sum;       /* [F][B][slots][chunks] partial sums of squared normalised timestamps (fixed-order reduction) */
     int *acc_nnz;          /* [F][B][slots][chunks] partial counts of pixels with at least one event */
-    float *den;            /* [F][B][slots] nnz + 1e-9 (or 1)                          */
+    float *den;            /* [F][B][slots] nnz + 1e-9 (or 1), followed by 2 floats: scale and 1/scale of the deterministic mode's
+                              flow-gradient words (written by the backward call)                                  */
     float *loss;           /* [1] scalar loss                                          */
     const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
     /* workspace written by the forward call and read by the backward call (sizes from tef_cm_sizes) */
@@ -79,12 +81,17 @@ typedef struct tef_cm_desc {
     int hist_done;         /* 1: every tef_update_pass of this window already counted its events into sort_bins (fused histogram),
                               the forward call then skips its own histogram pass */
     int reserved_;
+    /* optional quad-cell copies (NULL: not used).  The 2x2 neighbourhood of an in-image position is one 32-byte cell
+       {row y0: (left, right), row y0+1: (left, right)} of float2 pixels, stored once per parity (x0 & 1, y0 & 1):
+       [py*2+px][H/2+1][W/2+1] cells per map -- a bilinear sample / corner quad is a single 256-bit gather (one sector) */
+    const void *flowq;     /* [F][P][B] quad-cell flow maps, written by tef_update_pass (packedq); Iterative only       */
+    void *gimgq;           /* [F][B][slots][pol] quad-cell gradient images, written by tef_iterative_backward; sizes: out[11] */
 } tef_cm_desc;
 
-/* buffer sizes for the events currently described by `d`; out[11] =
+/* buffer sizes for the events currently described by `d`; out[13] =
    { slots, floats in img, floats in gflow, ints in sort_bins, ints in sort_sums, rows of sorted_ev,
      gradient-carrying rows, floats in posbuf, padded row length Wp, chunks per image (acc_sum / acc_nnz),
-     floats in gimg } */
+     floats in gimg, floats in gimgq (Iterative, non-deterministic; else 0), floats in flowq (likewise) } */
 int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out);
 /* number of image slots (temporal scale x sub-window x reference time, loss/flow.py:657-668) of the configuration in `d`,
    or the negative TEF_E* code the forward call would return for it */
@@ -102,7 +109,9 @@ int tef_stage_events(void *events_inout, const void *pol_mask, void *ev_out, voi
 int tef_pack_flow(const void *const *flow_maps_host, int F, int t, int P, int B, int H, int W,
                   void *packed, void *stream);
 /* backward counterpart: packed gradient -> [P][F][B][2][H][W] */
-int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream);
+/* det_scale: deterministic mode only -- the power-of-two scale of the fixed-point words, den[F*B*slots] of the backward call
+   (NULL = 1; ignored otherwise) */
+int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, const float *det_scale, void *stream);
 
 /* The whole of Iterative.update / Linear.update in one call and one launch: tef_pack_flow for the F maps of pass `t`
    plus tef_stage_events for the gradient-carrying set [0] and the detached set [1]; optionally the staging kernel also
@@ -111,6 +120,7 @@ typedef struct tef_update_desc {
     int F, t, P, B, H, W;
     const void *flow_maps[TEF_MAX_FLOWS];  /* [B][2][H][W] each                                   */
     void *packed;                          /* [F][P][B][2][H+1][Wp] float2                        */
+    void *packedq;                         /* optional quad-cell copy [F][P][B][4][H/2+1][W/2+1][8] floats (tef_cm_desc.flowq) or NULL */
     void *events[2];                       /* caller's [B][n][4]; ts += pass_index in place       */
     const void *masks[2];                  /* [B][n][2]                                           */
     void *ev_out[2];                       /* staged rows float4                                  */

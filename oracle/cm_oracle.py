@@ -221,24 +221,32 @@ def compute_pol_iwe(flow, event_list, res, pol_mask, round_idx=True, round_flow=
     return np.concatenate([pos, neg], 1)
 
 
-def events_to_image(xs, ys, ps, sensor_size=(180, 240), dtype=np.float32):
+def _enc_check(rc, sensor_size):
+    if rc != 0:
+        raise IndexError("event coordinates out of bounds for a sensor of size %s (reference: index_put_ raises IndexError)" % (tuple(sensor_size),))
+
+
+def events_to_image(xs, ys, ps, sensor_size=(180, 240), accumulate=True, dtype=np.float32):
     xs, ys, ps = _np(xs, dtype), _np(ys, dtype), _np(ps, dtype)
     img = np.zeros(tuple(sensor_size), dtype)
-    getattr(lib(), "orc_events_to_image_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ps), _ptr(img), ctypes.c_long(xs.size), int(sensor_size[0]), int(sensor_size[1]))
+    _enc_check(getattr(lib(), "orc_events_to_image_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ps), _ptr(img), ctypes.c_long(xs.size), int(sensor_size[0]),
+                                                                     int(sensor_size[1]), int(bool(accumulate))), sensor_size)
     return img
 
 
 def events_to_channels(xs, ys, ps, sensor_size=(180, 240), dtype=np.float32):
     xs, ys, ps = _np(xs, dtype), _np(ys, dtype), _np(ps, dtype)
     out = np.zeros((2,) + tuple(sensor_size), dtype)
-    getattr(lib(), "orc_events_to_channels_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ps), _ptr(out), ctypes.c_long(xs.size), int(sensor_size[0]), int(sensor_size[1]))
+    _enc_check(getattr(lib(), "orc_events_to_channels_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ps), _ptr(out), ctypes.c_long(xs.size), int(sensor_size[0]),
+                                                                        int(sensor_size[1])), sensor_size)
     return out
 
 
 def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240), dtype=np.float32):
     xs, ys, ts, ps = _np(xs, dtype), _np(ys, dtype), _np(ts, dtype), _np(ps, dtype)
     out = np.zeros((num_bins,) + tuple(sensor_size), dtype)
-    getattr(lib(), "orc_events_to_voxel_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ts), _ptr(ps), _ptr(out), ctypes.c_long(xs.size), int(num_bins), int(sensor_size[0]), int(sensor_size[1]))
+    _enc_check(getattr(lib(), "orc_events_to_voxel_" + _sfx(dtype))(_ptr(xs), _ptr(ys), _ptr(ts), _ptr(ps), _ptr(out), ctypes.c_long(xs.size), int(num_bins),
+                                                                     int(sensor_size[0]), int(sensor_size[1])), sensor_size)
     return out
 
 

@@ -814,14 +814,31 @@ void FN(orc_deblur_events)(const REAL *flow, const REAL *ev, const REAL *pol, RE
     }
 }
 
-/* dataloader/encodings.py:8-29; img [H][W] += ps at (ys.long(), xs.long()) */
-void FN(orc_events_to_image)(const REAL *xs, const REAL *ys, const REAL *ps, REAL *img, long n, int H, int W)
+/* index_put_ semantics of img[ys.long(), xs.long()] (dataloader/encodings.py:23-27): truncate toward zero, negative indices
+   wrap once like Python indexing, anything still outside raises IndexError (return -1 here; the wrapper raises) */
+static int FN(enc_pixel)(REAL xf, REAL yf, int H, int W, size_t *px)
+{
+    long x = (long)xf, y = (long)yf;
+    if (x < 0) x += W;
+    if (y < 0) y += H;
+    if (x < 0 || x >= W || y < 0 || y >= H) return -1;
+    *px = (size_t)y * W + (size_t)x;
+    return 0;
+}
+/* dataloader/encodings.py:8-29; img [H][W] (+)= ps at (ys.long(), xs.long()); accumulate = 0: plain put, events in order
+   (the last event of a pixel wins, like index_put_'s CPU kernel) */
+int FN(orc_events_to_image)(const REAL *xs, const REAL *ys, const REAL *ps, REAL *img, long n, int H, int W, int accumulate)
 {
     memset(img, 0, sizeof(REAL) * (size_t)H * W);
-    for (long i = 0; i < n; ++i) img[(size_t)(long)ys[i] * W + (long)xs[i]] += ps[i];
+    for (long i = 0; i < n; ++i) {
+        size_t px;
+        if (FN(enc_pixel)(xs[i], ys[i], H, W, &px)) return -1;
+        if (accumulate) img[px] += ps[i]; else img[px] = ps[i];
+    }
+    return 0;
 }
 /* dataloader/encodings.py:59-81; out [2][H][W] */
-void FN(orc_events_to_channels)(const REAL *xs, const REAL *ys, const REAL *ps, REAL *out, long n, int H, int W)
+int FN(orc_events_to_channels)(const REAL *xs, const REAL *ys, const REAL *ps, REAL *out, long n, int H, int W)
 {
     const size_t HW = (size_t)H * W;
     memset(out, 0, sizeof(REAL) * 2 * HW);
@@ -829,12 +846,14 @@ void FN(orc_events_to_channels)(const REAL *xs, const REAL *ys, const REAL *ps, 
         REAL p = ps[i];
         REAL mpos = p < (REAL)0 ? (REAL)0 : (p > (REAL)0 ? (REAL)1 : p);
         REAL mneg = p > (REAL)0 ? (REAL)0 : (p < (REAL)0 ? (REAL)-1 : p);
-        size_t px = (size_t)(long)ys[i] * W + (long)xs[i];
+        size_t px;
+        if (FN(enc_pixel)(xs[i], ys[i], H, W, &px)) return -1;
         out[px] += p * mpos; out[HW + px] += p * mneg;
     }
+    return 0;
 }
 /* dataloader/encodings.py:32-56; out [bins][H][W] */
-void FN(orc_events_to_voxel)(const REAL *xs, const REAL *ys, const REAL *ts, const REAL *ps, REAL *out, long n, int bins, int H, int W)
+int FN(orc_events_to_voxel)(const REAL *xs, const REAL *ys, const REAL *ts, const REAL *ps, REAL *out, long n, int bins, int H, int W)
 {
     const size_t HW = (size_t)H * W;
     memset(out, 0, sizeof(REAL) * (size_t)bins * HW);
@@ -842,8 +861,11 @@ void FN(orc_events_to_voxel)(const REAL *xs, const REAL *ys, const REAL *ts, con
         REAL t = ts[i] * (REAL)(bins - 1);
         REAL u = (REAL)1 - R_FABS(t - (REAL)b);
         REAL wgt = u > (REAL)0 ? u : (REAL)0;
-        out[(size_t)b * HW + (size_t)(long)ys[i] * W + (long)xs[i]] += ps[i] * wgt;
+        size_t px;
+        if (FN(enc_pixel)(xs[i], ys[i], H, W, &px)) return -1;
+        out[(size_t)b * HW + px] += ps[i] * wgt;
     }
+    return 0;
 }
 
 /* get_hot_event_mask -- NOT in the reference: PARITY UNPINNED.  Restates the published routine of tudelft/event_flow

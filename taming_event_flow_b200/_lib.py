@@ -63,6 +63,8 @@ class CmDesc(ctypes.Structure):
             ("gimg", ctypes.c_void_p),
             ("hist_done", ctypes.c_int),
             ("reserved_", ctypes.c_int),
+            ("flowq", ctypes.c_void_p),
+            ("gimgq", ctypes.c_void_p),
         ]
     )
 
@@ -74,6 +76,7 @@ class UpdateDesc(ctypes.Structure):
         + [
             ("flow_maps", ctypes.c_void_p * MAX_FLOWS),
             ("packed", ctypes.c_void_p),
+            ("packedq", ctypes.c_void_p),
             ("events", ctypes.c_void_p * 2),
             ("masks", ctypes.c_void_p * 2),
             ("ev_out", ctypes.c_void_p * 2),

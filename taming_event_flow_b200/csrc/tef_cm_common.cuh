@@ -58,14 +58,31 @@ struct ScaleTable {
 struct ImgGeom {
     int Wp;          // padded row length (even, >= W + 2)
     long plane;      // H * Wp
+    long lo_off;     // deterministic mode: distance (in int64 words) from a value's high word to its low word (see to_fix2)
 };
 
-// Deterministic mode: every accumulation (images, flow-gradient maps) is done in 64-bit fixed point (2^-40 resolution)
-// with integer reductions, which are associative, so results are bit-reproducible run to run and independent of the
-// event order; the per-image reductions use fixed-order partial sums in both modes.
+// Deterministic mode: every accumulation (images, flow-gradient maps) is done in 64-bit fixed point with integer reductions,
+// which are associative, so results are bit-reproducible run to run and independent of the event order; the per-image
+// reductions use fixed-order partial sums in both modes.
+//  * Images: TWO words per value.  high = v rounded to 2^-40, low = the remainder (|.| <= 2^-41, exact in double) at 2^-88.
+//    Every fp32 weight (>= 2^-48, 24-bit mantissa) is represented EXACTLY, so the sum is the exact sum of the reference's
+//    addends, rounded to fp32 once: pixels that only ever receive tiny corner weights (1e-10 happens: the diagonal neighbour
+//    of an event displaced by 1e-5 px) keep full relative precision, which a single 2^-40 word does not give them -- and
+//    those are the pixels with the largest gradients (dL/dIWE ~ 1/IWE).  The low word is non-zero only for weights below
+//    2^-16, so it costs a reduction only then.
+//  * Flow-gradient maps: one word at 2^-40 RELATIVE to a power-of-two scale derived from the upstream gradient and the
+//    per-image normalisers (det_scale_kernel), so the resolution does not depend on how the caller scales the loss.
 constexpr double kFixScale = 1099511627776.0;      // 2^40
+constexpr double kFixLoScale = 309485009821345068724781056.0;      // 2^88
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * kFixScale); }
 __device__ __forceinline__ float from_fix(long long v) { return (float)((double)v * (1.0 / kFixScale)); }
+__device__ __forceinline__ void to_fix2(float v, long long &hi, long long &lo) {
+    hi = __double2ll_rn((double)v * kFixScale);
+    lo = __double2ll_rn(((double)v - (double)hi * (1.0 / kFixScale)) * kFixLoScale);
+}
+__device__ __forceinline__ float from_fix2(long long hi, long long lo) {
+    return (float)((double)hi * (1.0 / kFixScale) + (double)lo * (1.0 / kFixLoScale));
+}
 __device__ __forceinline__ void red_add_i64(long long *addr, long long v) {
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
@@ -78,6 +95,8 @@ struct CmParams {
     float2 *gflow;
     float2 *img;             // deterministic mode: same layout with every float replaced by an int64 (twice the bytes)
     float2 *gimg;            // deterministic mode: gradient images [F][B][slot][phase][pol][H][Wp] float2 (otherwise in place in img)
+    const float4 *flowq;     // quad-cell copy of the flow maps [F][P][B][4][cplane] cells (2 float4 each) or nullptr
+    float4 *gimgq;           // quad-cell copy of the gradient images [F][B][slot][pol][4][cplane] cells or nullptr (written by iwe_grad_kernel)
     float2 *posbuf;          // [(P+1)][rows_grad] chain positions (x, y) of the gradient-carrying rows (Iterative)
     uint32_t *alivebuf;      // [F][rows_grad] cumulative in-image bits (bit tref)
     long rows_grad;
@@ -158,8 +177,13 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     p.flow = (const float2 *)d->flow; p.gflow = (float2 *)d->gflow; p.img = (float2 *)d->img;
     p.ig.Wp = (d->W + 3) & ~1; p.ig.plane = (long)d->H * p.ig.Wp;
     p.posbuf = (float2 *)d->posbuf; p.alivebuf = (uint32_t *)d->alivebuf;
+    // the quad-cell copies serve the one-hot fast paths of the Iterative kernels (not the deterministic mode, not Linear)
+    const bool quad_ok = !linear && !d->deterministic;
+    p.flowq = quad_ok ? (const float4 *)d->flowq : nullptr;
+    p.gimgq = (quad_ok && d->flowq) ? (float4 *)d->gimgq : nullptr;
     p.acc_sum = d->acc_sum; p.acc_nnz = d->acc_nnz; p.den = d->den; p.loss = d->loss; p.grad_out = d->grad_out;
     p.nslots = build_scales(d, linear, p.sc);
+    p.ig.lo_off = (long)p.F * p.B * p.nslots * 8 * p.ig.plane;      // the low words follow the high words of all images
     int ns = 0, blk = 0;
     for (int set = 0; set < 2; ++set)
         for (int t = 0; t < d->P; ++t) {
@@ -313,9 +337,10 @@ __device__ __forceinline__ void splat(float2 *__restrict__ slot_base, const Res 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (v[k] == 0.0f) continue;
-                    long long f = to_fix(v[k]);
-                    if (f == 0) f = v[k] > 0.0f ? 1 : -1;           // a non-zero contribution stays non-zero (nnz of focus_loss)
-                    red_add_i64(dst + k, f);
+                    long long hi, lo;
+                    to_fix2(v[k], hi, lo);                         // exact: a non-zero contribution stays non-zero (nnz of focus_loss)
+                    if (hi != 0) red_add_i64(dst + k, hi);
+                    if (lo != 0) red_add_i64(dst + g.lo_off + k, lo);
                 }
             }
         }
@@ -485,10 +510,41 @@ __device__ __forceinline__ void iwe_grad_inside_1hot(const float2 *__restrict__ 
     }
 }
 
+// iwe_grad_inside_1hot on the quad-cell copy of the gradient images: `cells` = cells of (slot, polarity); both image rows of the
+// corner quad arrive in one 256-bit gather.  Entries of pixels outside the image are never written and never used (the right
+// column / bottom row tests below are the ones of iwe_grad_inside_1hot).
+__device__ __forceinline__ void iwe_grad_inside_1hot_quad(const float4 *__restrict__ cells, const Res &r, float2 p /* (x, y) */, float nts, float &gy,
+                                                          float &gx) {
+    const float2 c0 = make_float2(floorf(p.x), floorf(p.y));
+    const float2 p1 = add2(p, bc(1.0f));
+    const float2 c1 = make_float2(floorf(p1.x), floorf(p1.y));
+    const float2 d0 = sub2(p, c0), e1 = sub2(p, c1);
+    const float2 u0 = sub2(bc(1.0f), make_float2(fabsf(d0.x), fabsf(d0.y)));
+    const float2 u1 = sub2(bc(1.0f), make_float2(fabsf(e1.x), fabsf(e1.y)));
+    const float wx0 = fmaxf(0.0f, u0.x), wy0 = fmaxf(0.0f, u0.y), wx1 = fmaxf(0.0f, u1.x), wy1 = fmaxf(0.0f, u1.y);
+    const float dx0 = d0.x > 0.0f ? -1.0f : -0.0f, dy0 = d0.y > 0.0f ? -1.0f : -0.0f;
+    const float dx1 = u1.x > 0.0f ? 1.0f : (u1.x == 0.0f ? 0.5f : 0.0f), dy1 = u1.y > 0.0f ? 1.0f : (u1.y == 0.0f ? 0.5f : 0.0f);
+    float4 v, w;
+    load_quad(cells, quad_cell(r, (int)c0.y, (int)c0.x), v, w);
+    const bool okx1 = c1.x <= r.wm1;
+    {
+        const float gl = v.x + nts * v.y, gr = v.z + nts * v.w;
+        gy += gl * dy0 * wx0; gx += gl * wy0 * dx0;
+        if (okx1) { gy += gr * dy0 * wx1; gx += gr * wy0 * dx1; }
+    }
+    if (c1.y <= r.hm1) {
+        const float gl = w.x + nts * w.y, gr = w.z + nts * w.w;
+        gy += gl * dy1 * wx0; gx += gl * wy1 * dx0;
+        if (okx1) { gy += gr * dy1 * wx1; gx += gr * wy1 * dx1; }
+    }
+}
+
 // dL/dmap of one bilinear flow sample: two 16-byte reductions (one per tap row)
 // into the dual-phase packed gradient map; c_k = dt * w_k, value = c_k * (g_x, g_y).
+// DET: `ginv` = 1 / (power-of-two scale of the flow-gradient words), see det_scale_kernel
 template <bool DET>
-__device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const ImgGeom &g, const Taps &tp, float dt, float gpy, float gpx) {
+__device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const ImgGeom &g, const Taps &tp, float dt, float gpy, float gpx,
+                                         float ginv = 1.0f) {
     if (tp.x0 < -1) return;                                         // sample outside the map: all taps invalid
     const int phase = tp.x0 & 1;
     const int col = tp.x0 + phase;
@@ -506,7 +562,7 @@ __device__ __forceinline__ void taps_red(float2 *__restrict__ gmap_phase0, const
             const float v[4] = { cl * gpx, cl * gpy, cr * gpx, cr * gpy };
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (v[k] != 0.0f) red_add_i64(dst + k, to_fix(v[k]));
+                if (v[k] != 0.0f) red_add_i64(dst + k, __double2ll_rn((double)v[k] * (double)ginv * kFixScale));
         }
     }
 }

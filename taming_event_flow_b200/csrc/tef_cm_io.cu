@@ -60,8 +60,8 @@ struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
 
 // [B][2][H][W] planar (ch0 = x, ch1 = y) -> dual-phase float2 [B][phase][H+1][Wp] with zero padding (tef_device.cuh);
 // bx CTAs walk one (flow scale f, sample b) map
-__device__ __forceinline__ void pack_flow_body(const FlowPtrs &src, float2 *__restrict__ packed, int t, int P, int B, const Res &r,
-                                               int f, int b, int xblk, int bx) {
+__device__ __forceinline__ void pack_flow_body(const FlowPtrs &src, float2 *__restrict__ packed, float4 *__restrict__ packedq, int t, int P, int B,
+                                               const Res &r, int f, int b, int xblk, int bx) {
     const long HW = (long)r.H * r.W;
     const float *sx = src.p[f] + (long)b * 2 * HW, *sy = sx + HW;
     float2 *dst = packed + (((long)f * P + t) * B + b) * 2 * r.fplane;
@@ -73,23 +73,41 @@ __device__ __forceinline__ void pack_flow_body(const FlowPtrs &src, float2 *__re
         const bool in = (y < r.H) && (x >= 0) && (x < r.W);
         dst[i] = in ? make_float2(sx[y * r.W + x], sy[y * r.W + x]) : make_float2(0.f, 0.f);
     }
+    if (!packedq) return;
+    // quad-cell copy (tef_device.cuh, quad_cell): cell (Y, X) of parity (px, py) holds rows 2Y-py, 2Y-py+1 x columns 2X-px, 2X-px+1
+    float4 *dq = packedq + (((long)f * P + t) * B + b) * 8 * r.cplane;
+    const int ncell = 4 * r.cplane;
+    for (int i = xblk * kThreads + threadIdx.x; i < ncell; i += bx * kThreads) {
+        const int ph = i / r.cplane, c = i - ph * r.cplane;
+        const int Y = c / r.CX, X = c - Y * r.CX;
+        const int y = 2 * Y - (ph >> 1), x = 2 * X - (ph & 1);
+        float2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = y + (k >> 1), xx = x + (k & 1);
+            const bool in = (yy >= 0) && (yy < r.H) && (xx >= 0) && (xx < r.W);
+            v[k] = in ? make_float2(sx[yy * r.W + xx], sy[yy * r.W + xx]) : make_float2(0.f, 0.f);
+        }
+        dq[2 * (long)i] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        dq[2 * (long)i + 1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+    }
 }
 __global__ void __launch_bounds__(kThreads) pack_flow_kernel(const __grid_constant__ FlowPtrs src, float2 *__restrict__ packed, int t, int P,
                                                              int B, Res r) {
-    pack_flow_body(src, packed, t, P, B, r, blockIdx.z, blockIdx.y, blockIdx.x, gridDim.x);
+    pack_flow_body(src, packed, nullptr, t, P, B, r, blockIdx.z, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // Iterative.update / Linear.update in ONE launch: CTAs [0, nb_stage) stage (and count) the events, the rest pack the flow maps
-struct PackArgs { FlowPtrs src; float2 *packed; int t, P, B, F, bx; Res r; };
+struct PackArgs { FlowPtrs src; float2 *packed; float4 *packedq; int t, P, B, F, bx; Res r; };
 __global__ void __launch_bounds__(kThreads) update_pass_kernel(const __grid_constant__ StageTwo s, const __grid_constant__ PackArgs k, int nb_stage) {
     if ((int)blockIdx.x < nb_stage) { stage_two_body(s, blockIdx.x); return; }
     const int pb = blockIdx.x - nb_stage;
-    pack_flow_body(k.src, k.packed, k.t, k.P, k.B, k.r, pb / (k.bx * k.B), (pb / k.bx) % k.B, pb % k.bx, k.bx);
+    pack_flow_body(k.src, k.packed, k.packedq, k.t, k.P, k.B, k.r, pb / (k.bx * k.B), (pb / k.bx) % k.B, pb % k.bx, k.bx);
 }
 
 template <bool DET>
 __global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__restrict__ packed, float *__restrict__ out, int F, int P, int B,
-                                                               int W, long HW, ImgGeom g) {
+                                                               int W, long HW, ImgGeom g, const float *__restrict__ det_scale) {
     const int fp = blockIdx.z, b = blockIdx.y;
     const int f = fp / P, t = fp % P;
     const float2 *src = packed + (((long)f * P + t) * B + b) * (DET ? 4 : 2) * g.plane;
@@ -102,7 +120,8 @@ __global__ void __launch_bounds__(kThreads) unpack_grad_kernel(const float2 *__r
         } else {
             const longlong2 *q = reinterpret_cast<const longlong2 *>(src);
             const longlong2 a = q[o], c = q[g.plane + o + 1];
-            ox[i] = from_fix(a.x + c.x); oy[i] = from_fix(a.y + c.y);
+            const double sc = (det_scale ? (double)__ldg(det_scale) : 1.0) * (1.0 / kFixScale);      // power of two: exact
+            ox[i] = (float)((double)(a.x + c.x) * sc); oy[i] = (float)((double)(a.y + c.y) * sc);
         }
     }
 }
@@ -134,15 +153,16 @@ extern "C" int tef_pack_flow(const void *const *flow_maps_host, int F, int t, in
     return (int)cudaGetLastError();
 }
 
-extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, void *stream) {
+extern "C" int tef_unpack_flow_grad(const void *packed, void *out, int F, int P, int B, int H, int W, int deterministic, const float *det_scale,
+                                    void *stream) {
     if (!packed || !out || F < 1 || P < 1 || B < 1) return TEF_EINVAL;
     const long HW = (long)H * W;
     int bx = (int)((HW + kThreads - 1) / kThreads);
     if (bx > 148 * 4) bx = 148 * 4;
     ProfScope ps(K_UNPACK_GRAD, (cudaStream_t)stream);
-    ImgGeom g; g.Wp = (W + 3) & ~1; g.plane = (long)H * g.Wp;
-    if (deterministic) unpack_grad_kernel<true><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
-    else unpack_grad_kernel<false><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g);
+    ImgGeom g; g.Wp = (W + 3) & ~1; g.plane = (long)H * g.Wp; g.lo_off = 0;
+    if (deterministic) unpack_grad_kernel<true><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g, det_scale);
+    else unpack_grad_kernel<false><<<dim3(bx, B, F * P), kThreads, 0, (cudaStream_t)stream>>>((const float2 *)packed, (float *)out, F, P, B, W, HW, g, nullptr);
     return (int)cudaGetLastError();
 }
 
@@ -150,11 +170,11 @@ extern "C" int tef_update_pass(const tef_update_desc *u, void *stream) {
     if (!u) return TEF_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     PackArgs k;
-    k.F = 0; k.bx = 0; k.B = u->B;
+    k.F = 0; k.bx = 0; k.B = u->B; k.packedq = nullptr;
     if (u->F > 0) {
         if (!u->packed || u->F > TEF_MAX_FLOWS || u->t < 0 || u->t >= u->P || u->B < 1) return TEF_EINVAL;
         for (int f = 0; f < u->F; ++f) { if (!u->flow_maps[f]) return TEF_EINVAL; k.src.p[f] = (const float *)u->flow_maps[f]; }
-        k.packed = (float2 *)u->packed; k.t = u->t; k.P = u->P; k.F = u->F; k.r = Res::make(u->H, u->W);
+        k.packed = (float2 *)u->packed; k.packedq = (float4 *)u->packedq; k.t = u->t; k.P = u->P; k.F = u->F; k.r = Res::make(u->H, u->W);
         k.bx = (2 * k.r.fplane + kThreads - 1) / kThreads;
         if (k.bx > 148 * 4) k.bx = 148 * 4;
     }

@@ -41,28 +41,34 @@ namespace tef {
 // ---------------------------------------------------------------------------------
 // One chain step from position q = (x, y): sample the map, move by dt * flow (utils/iwe.py:14).  The move stays scalar:
 // ptxas contracts a packed product feeding a packed sum into FFMA2 (see tef_device.cuh), the reference rounds twice.
-__device__ __forceinline__ float2 chain_step(const float2 *__restrict__ map, const Res &r, float2 q, float dt, bool safe) {
+// QUAD: `map` walks the quad-cell copies (one 256-bit gather per sample); only the event's own location can lie outside the
+// sensor, and that first step of either chain samples the map of the event's own pass, `own` (dual-phase rows, generic sample).
+template <bool QUAD>
+__device__ __forceinline__ float2 chain_step(const float2 *__restrict__ map, const float2 *__restrict__ own, const Res &r, float2 q, float dt, bool safe) {
     float2 v;                                          // (x-flow, y-flow)
-    if (safe) v = sample_flow_inside_xy<false>(map, r, q, nullptr);
-    else v = sample_flow<false>(map, r, q.y, q.x, nullptr);
+    if (safe) v = sample_flow_inside_xy<false, QUAD>(map, r, q, nullptr);
+    else v = sample_flow<false>(QUAD ? own : map, r, q.y, q.x, nullptr);
     return make_float2(q.x + dt * v.x, q.y + dt * v.y);
 }
-__device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* maps of (f, sample b), pass 0 */,
+template <bool QUAD>
+__device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *__restrict__ flow_fb /* dual-phase maps of (f, sample b), pass 0 */,
+                                               const float2 *__restrict__ walk_fb /* what the chain walks: flow_fb, or the quad-cell copies of (f, b), pass 0 */,
                                                int t, float ts, float y0, float x0, float2 *__restrict__ pos /* [P+1][kThreads], (x, y) */,
                                                float2 *__restrict__ pb /* this row of posbuf (stride rows_grad) or nullptr */,
                                                int keep_lo, int keep_hi /* nodes some scale splats for this pass; the others only feed the mask */) {
-    const long stride = (long)p.B * 2 * p.res.fplane;   // one pass further (dual-phase maps)
+    const long stride = QUAD ? (long)p.B * 16 * p.res.cplane : (long)p.B * 2 * p.res.fplane;   // one pass further, in float2 units
+    const float2 *own = flow_fb + (long)t * p.B * 2 * p.res.fplane;
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
     const bool in0 = inside(y0, x0, p.res);
     float2 q = make_float2(x0, y0);
     float tprev = ts;
     bool al = true, safe = in0;
-    const float2 *map = flow_fb + (long)t * stride;
+    const float2 *map = walk_fb + (long)t * stride;
     float2 *pw = pos + (t + 1) * kThreads + threadIdx.x;
     for (int tr = t + 1; tr <= p.P; ++tr, map += stride, pw += kThreads) {   // forward: sample map tr-1, land on node tr
         if (al) {
-            q = chain_step(map, p.res, q, (float)tr - tprev, safe);
+            q = chain_step<QUAD>(map, own, p.res, q, (float)tr - tprev, safe);
             al = inside(q.y, q.x, p.res);              // utils/iwe.py:52-59
             if (al) alive |= (1u << tr);
             safe = true;
@@ -74,11 +80,11 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
         }
     }
     q = make_float2(x0, y0); tprev = ts; al = true; safe = in0;
-    map = flow_fb + (long)t * stride;
+    map = walk_fb + (long)t * stride;
     pw = pos + t * kThreads + threadIdx.x;
     for (int tr = t; tr >= 0; --tr, map -= stride, pw -= kThreads) {         // backward: sample map tr, land on node tr
         if (al) {
-            q = chain_step(map, p.res, q, (float)tr - tprev, safe);
+            q = chain_step<QUAD>(map, own, p.res, q, (float)tr - tprev, safe);
             al = inside(q.y, q.x, p.res);
             if (al) alive |= (1u << tr);
             safe = true;
@@ -127,7 +133,7 @@ __device__ __forceinline__ uint32_t active_scales(const CmParams &p, const WinS 
     return has;
 }
 
-template <bool DET>
+template <bool DET, bool QUAD>
 __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(const __grid_constant__ CmParams p) {
     extern __shared__ float2 pos[];
     __shared__ WinS sw[TEF_MAX_SCALES];
@@ -145,7 +151,9 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
         int keep_lo = p.P + 1, keep_hi = -1;
         for (int s = 0; s < p.sc.S; ++s)
             if (sw[s].valid) { keep_lo = min(keep_lo, sw[s].tr0); keep_hi = max(keep_hi, sw[s].tr1); }
-        alive = warp_chain(p, p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane, t, e.x, e.y, e.z, pos, pb, keep_lo, keep_hi);
+        const float2 *flow_fb = p.flow + ((long)f * p.P * p.B + b) * 2 * p.res.fplane;
+        const float2 *walk_fb = QUAD ? reinterpret_cast<const float2 *>(p.flowq + ((long)f * p.P * p.B + b) * 8 * p.res.cplane) : flow_fb;
+        alive = warp_chain<QUAD>(p, flow_fb, walk_fb, t, e.x, e.y, e.z, pos, pb, keep_lo, keep_hi);
         if (pb) p.alivebuf[(long)f * p.rows_grad + row] = alive;
         has = active_scales(p, sw, alive);
         img_fb = p.img + ((long)f * p.B + b) * p.nslots * slot_stride;
@@ -187,11 +195,11 @@ __global__ void __launch_bounds__(kThreads, TEF_FWD_MIN_BLOCKS) iter_fwd_kernel(
 // one reverse chain step: reduce dL/dmap, return dL/d(source position)
 template <bool DET>
 __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
-                                         float sx, float dt, float gpy, float gpx, float &cy_, float &cx_) {
+                                         float sx, float dt, float gpy, float gpx, float &cy_, float &cx_, float ginv = 1.0f) {
     Taps tp;
     if (inside(sy, sx, r)) sample_flow_inside<true>(map, r, sy, sx, &tp);
     else sample_flow<true>(map, r, sy, sx, &tp);
-    taps_red<DET>(gmap, g, tp, dt, gpy, gpx);
+    taps_red<DET>(gmap, g, tp, dt, gpy, gpx, ginv);
     const float dvy_dy = (1.0f - tp.ax) * (tp.v[2].y - tp.v[0].y) + tp.ax * (tp.v[3].y - tp.v[1].y);
     const float dvy_dx = (1.0f - tp.ay) * (tp.v[1].y - tp.v[0].y) + tp.ay * (tp.v[3].y - tp.v[2].y);
     const float dvx_dy = (1.0f - tp.ax) * (tp.v[2].x - tp.v[0].x) + tp.ax * (tp.v[3].x - tp.v[1].x);
@@ -205,18 +213,21 @@ __device__ __forceinline__ void step_bwd(const float2 *__restrict__ map, float2 
 // push through the step; the others only take part in the shuffles.  A row is reduced when its merged values are not all
 // zero: a row outside the map (or with zero weights) carries zeros in every lane of the cell, and adding zeros is a no-op.
 // Must be called by all 32 lanes.  Non-deterministic mode only.
-__device__ __forceinline__ void step_bwd_warp(const float2 *__restrict__ map, float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
+template <bool QUAD>
+__device__ __forceinline__ void step_bwd_warp(const float2 *__restrict__ map, const CmParams &p, long own_index /* ((f * P + t) * B + b): the event's own pass */,
+                                              float2 *__restrict__ gmap, const Res &r, const ImgGeom &g, float sy,
                                               float sx, float dt, float gpy, float gpx, float &cy_, float &cx_, bool on, unsigned lane,
                                               unsigned key_base /* sample * map size */) {
-    if (on && !inside(sy, sx, r)) {                 // an event whose own location lies outside the sensor: generic sample, not merged
-        step_bwd<false>(map, gmap, r, g, sy, sx, dt, gpy, gpx, cy_, cx_);
+    if (on && !inside(sy, sx, r)) {                 // an event whose own location lies outside the sensor (first step only): generic sample, not merged
+        // (with QUAD `map` walks the quad-cell copies; the generic sample reads the dual-phase rows of the event's own pass)
+        step_bwd<false>(QUAD ? p.flow + own_index * 2 * r.fplane : map, gmap, r, g, sy, sx, dt, gpy, gpx, cy_, cx_);
         on = false;
     }
     float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
     unsigned off = 0;
     if (on) {
         Taps tp;
-        sample_flow_inside<true>(map, r, sy, sx, &tp);
+        sample_flow_inside<true, QUAD>(map, r, sy, sx, &tp);
         const int phase = tp.x0 & 1;
         off = (unsigned)(phase * (int)g.plane + tp.y0 * g.Wp + tp.x0 + phase);
         // taps_red's coefficients and values, and step_bwd's Jacobian, on packed fp32x2 arithmetic: same products, rounded
@@ -246,7 +257,7 @@ __device__ __forceinline__ void step_bwd_warp(const float2 *__restrict__ map, fl
 // next node, reduce into the packed flow-gradient map and step towards the event's own window.
 // The node loops run over the CTA-uniform range of nodes any scale splats for this pass, and (outside the deterministic
 // mode) threads without an event or without a gradient stay in them for the warp-level merge of the reductions.
-template <bool DET>
+template <bool DET, bool QUAD>
 __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(const __grid_constant__ CmParams p) {
     __shared__ WinS sw[TEF_MAX_SCALES];
     int t, b, row, set; float4 e; float2 m;
@@ -254,8 +265,9 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     build_windows(p, t, sw);
     if (DET && !live) return;
     const int f = blockIdx.y;
-    const long HW = 2 * p.res.fplane;                              // float2 elements per (pass, sample) flow map
-    const float2 *flow_f = p.flow + (long)f * p.P * p.B * HW;
+    const long HW = 2 * p.res.fplane;                              // float2 elements per (pass, sample) dual-phase flow map
+    const long HWq = QUAD ? 16 * (long)p.res.cplane : HW;          // ... of what the steps sample (quad-cell copy or the same)
+    const float2 *flow_f = QUAD ? reinterpret_cast<const float2 *>(p.flowq) + (long)f * p.P * p.B * HWq : p.flow + (long)f * p.P * p.B * HW;
     const long gmap_sz = (DET ? 4 : 2) * p.ig.plane;               // float2 elements per (pass, sample) gradient map
     float2 *gflow_f = p.gflow + (long)f * p.P * p.B * gmap_sz;
     uint32_t alive = 0, has = 0;
@@ -289,10 +301,16 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     // the loader's one-hot masks read one polarity plane and skip the mask products
     const bool onehot = (m.x == 1.0f && m.y == 0.0f) || (m.x == 0.0f && m.y == 1.0f);
     const float2 *img_pol = img_fb + (m.x != 0.0f ? 0 : p.ig.plane);
+    // quad-cell gradient images of this sample: [slot][pol][4][cplane] cells of two float4
+    const float4 *gq_pol = QUAD ? p.gimgq + ((((long)f * p.B + b) * p.nslots) * 2 + (m.x != 0.0f ? 0 : 1)) * 8 * p.res.cplane : nullptr;
+    const long own_index = ((long)f * p.P + t) * p.B + b;
     auto node_grad = [&](int tr, float2 q, float &gy, float &gx) {
         if (tr >= w0_tr0 && tr <= w0_tr1) {
             const float nts = 1.0f - div_const(fabsf((float)tr - ts), w0_fdelta, w0_rdelta);
-            if (onehot) iwe_grad_inside_1hot(img_pol + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q, nts, gy, gx);
+            if (onehot) {
+                if constexpr (QUAD) iwe_grad_inside_1hot_quad(gq_pol + (long)(w0_slot0 + tr) * 16 * p.res.cplane, p.res, q, nts, gy, gx);
+                else iwe_grad_inside_1hot(img_pol + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q, nts, gy, gx);
+            }
             else iwe_grad<true>(img_fb + (long)(w0_slot0 + tr) * gslot, p.res, p.ig, q.y, q.x, nts, m, gy, gx);
         }
         for (int s = 1; s < p.sc.S; ++s) {
@@ -302,13 +320,14 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
         }
     };
 
-    const long map_stride = (long)p.B * HW, gmap_stride = (long)p.B * gmap_sz;
+    const long map_stride = (long)p.B * HWq, gmap_stride = (long)p.B * gmap_sz;
+    const float ginv = DET ? __ldg(p.den + p.F * p.B * p.nslots + 1) : 1.0f;     // 1 / scale of the fixed-point gradient words
     // reverse of the forward chain: nodes hi_node .. t+1 (nodes beyond carry no gradient)
     float cy_ = 0.f, cx_ = 0.f;
     {
         int tr = min(hi_node, p.P);
         const float2 *pq = pb + (long)tr * p.rows_grad;                  // position of node tr; one row_grad back: node tr-1
-        const float2 *map = flow_f + (long)(tr - 1) * map_stride + (long)b * HW;
+        const float2 *map = flow_f + (long)(tr - 1) * map_stride + (long)b * HWq;
         float2 *gmap = gflow_f + (long)(tr - 1) * gmap_stride + (long)b * gmap_sz;
         float2 q = (act && tr >= t + 1) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr >= t + 1; --tr, pq -= p.rows_grad, map -= map_stride, gmap -= gmap_stride) {
@@ -321,8 +340,8 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             const bool on = gpy != 0.f || gpx != 0.f;
             const float dt = first ? ((float)tr - ts) : 1.0f;
-            if (!DET) step_bwd_warp(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
-            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
+            if (!DET) step_bwd_warp<QUAD>(map, p, own_index, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
+            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, ginv);
             q = src;
         }
     }
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
     {
         int tr = max(lo_node, 0);
         const float2 *pq = pb + (long)tr * p.rows_grad;
-        const float2 *map = flow_f + (long)tr * map_stride + (long)b * HW;
+        const float2 *map = flow_f + (long)tr * map_stride + (long)b * HWq;
         float2 *gmap = gflow_f + (long)tr * gmap_stride + (long)b * gmap_sz;
         float2 q = (act && tr <= t) ? __ldcs(pq) : make_float2(0.f, 0.f);
         for (; tr <= t; ++tr, pq += p.rows_grad, map += map_stride, gmap += gmap_stride) {
@@ -344,8 +363,8 @@ __global__ void __launch_bounds__(kThreads, TEF_BWD_MIN_BLOCKS) iter_bwd_kernel(
             cy_ = 0.f; cx_ = 0.f;
             const bool on = gpy != 0.f || gpx != 0.f;
             const float dt = first ? ((float)tr - ts) : -1.0f;
-            if (!DET) step_bwd_warp(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
-            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_);
+            if (!DET) step_bwd_warp<QUAD>(map, p, own_index, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, on, lane, key_base);
+            else if (on) step_bwd<DET>(map, gmap, p.res, p.ig, src.y, src.x, dt, gpy, gpx, cy_, cx_, ginv);
             q = src;
         }
     }
@@ -372,14 +391,16 @@ static int launch_fwd(const CmParams &p, cudaStream_t st) {
         cudaGetDevice(&dev);
         if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
             const int mx = (int)(sizeof(float2) * (TEF_MAX_PASSES + 1) * kThreads);
-            cudaFuncSetAttribute(iter_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(iter_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(iter_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(iter_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(iter_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
         }
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_FWD, st);
-        if (p.det) iter_fwd_kernel<true><<<grid, kThreads, chain_smem(p), st>>>(p);
-        else iter_fwd_kernel<false><<<grid, kThreads, chain_smem(p), st>>>(p);
+        if (p.det) iter_fwd_kernel<true, false><<<grid, kThreads, chain_smem(p), st>>>(p);
+        else if (p.flowq) iter_fwd_kernel<false, true><<<grid, kThreads, chain_smem(p), st>>>(p);
+        else iter_fwd_kernel<false, false><<<grid, kThreads, chain_smem(p), st>>>(p);
     }
     return (int)cudaGetLastError();
 }
@@ -387,8 +408,9 @@ static int launch_bwd(const CmParams &p, cudaStream_t st) {
     if (p.seg.blk_off[p.seg.nseg] > 0) {
         dim3 grid(p.seg.blk_off[p.seg.nseg], p.F);
         ProfScope ps(K_ITER_BWD, st);
-        if (p.det) iter_bwd_kernel<true><<<grid, kThreads, 0, st>>>(p);
-        else iter_bwd_kernel<false><<<grid, kThreads, 0, st>>>(p);
+        if (p.det) iter_bwd_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
+        else if (p.flowq && p.gimgq) iter_bwd_kernel<false, true><<<grid, kThreads, 0, st>>>(p);
+        else iter_bwd_kernel<false, false><<<grid, kThreads, 0, st>>>(p);
     }
     return (int)cudaGetLastError();
 }
@@ -400,7 +422,7 @@ extern "C" int tef_iterative_forward(const tef_cm_desc *d, void *stream) {
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
     const long nimg = (long)p.F * p.B * p.nslots;
-    cudaMemsetAsync(p.img, 0, sizeof(float2) * nimg * (p.det ? 8 : 4) * p.ig.plane, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * nimg * (p.det ? 16 : 4) * p.ig.plane, st);     // deterministic: high and low words
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     rc = launch_fwd(p, st);

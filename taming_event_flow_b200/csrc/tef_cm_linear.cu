@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, 4) linear_bwd_kernel(const __grid_co
         gvy += dtl * gy; gvx += dtl * gx;
     }
     if (gvy == 0.f && gvx == 0.f) return;
-    taps_red<DET>(p.gflow + (((long)f * p.P + t) * p.B + b) * (DET ? 4 : 2) * p.ig.plane, p.ig, tp, 1.0f, gvy, gvx);
+    taps_red<DET>(p.gflow + (((long)f * p.P + t) * p.B + b) * (DET ? 4 : 2) * p.ig.plane, p.ig, tp, 1.0f, gvy, gvx,
+                  DET ? __ldg(p.den + p.F * p.B * p.nslots + 1) : 1.0f);
 }
 
 }  // namespace tef
@@ -95,7 +96,7 @@ extern "C" int tef_linear_forward(const tef_cm_desc *d, void *stream) {
     int rc = fill_params(d, 1, p);
     if (rc) return rc;
     if (!p.flow || !p.img || !p.acc_sum || !p.acc_nnz || !p.den || !p.loss) return TEF_EINVAL;
-    cudaMemsetAsync(p.img, 0, sizeof(float2) * (long)p.F * p.B * p.nslots * (p.det ? 8 : 4) * p.ig.plane, st);
+    cudaMemsetAsync(p.img, 0, sizeof(float2) * (long)p.F * p.B * p.nslots * (p.det ? 16 : 4) * p.ig.plane, st);   // deterministic: high and low words
     rc = tef_sort_events(p, st);
     if (rc) return rc;
     if (p.seg.blk_off[p.seg.nseg] > 0) {

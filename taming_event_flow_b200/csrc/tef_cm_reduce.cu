@@ -23,9 +23,10 @@ __device__ __forceinline__ float2 pixel_sum(const float2 *__restrict__ slot_base
         const float2 b = slot_base[(long)(2 + pol) * g.plane + o + 1];       // phase 1: column x + 1
         return make_float2(a.x + b.x, a.y + b.y);
     }
-    const longlong2 *q = reinterpret_cast<const longlong2 *>(slot_base);
+    const longlong2 *q = reinterpret_cast<const longlong2 *>(slot_base), *ql = q + g.lo_off / 2;
     const longlong2 a = q[(long)pol * g.plane + o], b = q[(long)(2 + pol) * g.plane + o + 1];
-    return make_float2(from_fix(a.x + b.x), from_fix(a.y + b.y));            // exact integer sum, one rounding
+    const longlong2 al = ql[(long)pol * g.plane + o], bl = ql[(long)(2 + pol) * g.plane + o + 1];
+    return make_float2(from_fix2(a.x + b.x, al.x + bl.x), from_fix2(a.y + b.y, al.y + bl.y));     // exact integer sums, one rounding
 }
 
 // per-CTA partial sums in a fixed slot (no atomics): the final per-image sum has a fixed order in both modes
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constan
     const float cf = upstream(__ldg(p.grad_out), p.F, p.sc.S, div_a, s) / p.den[image];
     float2 *im = p.img + image * (DET ? 8 : 4) * p.ig.plane;
     float2 *out = DET ? p.gimg + image * 4 * p.ig.plane : im;     // [phase][pol][H][Wp]; in place unless deterministic
+    float2 *outq = (!DET && p.gimgq) ? reinterpret_cast<float2 *>(p.gimgq) + image * 2 * 16 * p.res.cplane : nullptr;   // [pol][4][cplane] cells of 4 float2
     const long p0 = (long)blockIdx.x * kPixPerBlock;
     const long p1 = min(p0 + kPixPerBlock, HW);
     for (long i = p0 + threadIdx.x; i < p1; i += kThreads) {
@@ -120,7 +122,39 @@ __global__ void __launch_bounds__(kThreads) iwe_grad_kernel(const __grid_constan
             const float2 gv = make_float2(-(ga * (a / d)), ga / d);                    // (dL/dcount, dL/dtime-weighted)
             out[(long)pol * p.ig.plane + o] = gv;                                      // phase 0: column x
             out[(long)(2 + pol) * p.ig.plane + o + 1] = gv;                            // phase 1: column x + 1
+            if (!DET && outq) {
+                // quad-cell copy: the pixel is the (ry, rx) entry of one cell per parity (tef_device.cuh, quad_cell)
+                const int y = (int)(i / p.W), x = (int)(i % p.W);
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int yy = y + (ph >> 1), xx = x + (ph & 1);
+                    const long cell = (long)(pol * 4 + ph) * p.res.cplane + (yy >> 1) * p.res.CX + (xx >> 1);
+                    outq[cell * 4 + (yy & 1) * 2 + (xx & 1)] = gv;
+                }
+            }
         }
+    }
+}
+
+// Deterministic mode: power-of-two scale of the fixed-point flow-gradient words = the largest per-image factor
+// |upstream gradient / normaliser| rounded up, so that the normalised addends are O(weights x events per pixel) whatever the
+// caller multiplies the loss by.  den[nimg] = scale, den[nimg + 1] = 1 / scale (both exact powers of two).
+__global__ void det_scale_kernel(const __grid_constant__ CmParams p) {
+    const int nimg = p.F * p.B * p.nslots;
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < nimg; i += 32) {
+        const int s = scale_of_slot(p.sc, i % p.nslots);
+        const float div_a = p.linear ? 2.0f : (float)(2 * p.sc.delta[s] + 1);
+        m = fmaxf(m, fabsf(upstream(__ldg(p.grad_out), p.F, p.sc.S, div_a, s) / p.den[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+        int e = 0;
+        if (m > 0.0f && m < 3.0e38f) frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)
+        e = max(-100, min(100, e));
+        p.den[nimg] = ldexpf(1.0f, e);
+        p.den[nimg + 1] = ldexpf(1.0f, -e);
     }
 }
 
@@ -150,6 +184,7 @@ int tef_grad_images(const CmParams &p, cudaStream_t st) {
     const int nimg = p.F * p.B * p.nslots;
     dim3 grid((unsigned)p.nchunks, nimg);
     ProfScope ps(K_IWE_GRAD, st);
+    if (p.det) det_scale_kernel<<<1, 32, 0, st>>>(p);
     if (p.det) iwe_grad_kernel<true><<<grid, kThreads, 0, st>>>(p, HW);
     else iwe_grad_kernel<false><<<grid, kThreads, 0, st>>>(p, HW);
     return (int)cudaGetLastError();
@@ -171,7 +206,7 @@ extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     for (int s = 0; s < p.seg.nseg; ++s) r += (long)p.B * p.seg.n[s];
     out[0] = p.nslots;
     const long wide = p.det ? 2 : 1;                              // deterministic mode: int64 instead of float
-    out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 * wide;   // floats in img
+    out[1] = (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 * wide * wide;   // floats in img (deterministic: a high and a low int64 word per value)
     out[2] = (long)p.F * p.P * p.B * 2 * p.ig.plane * 2 * wide;        // floats in gflow
     out[3] = p.sort.nbins + 1;                                    // ints in sort_bins
     out[4] = p.sort.nbins / 2048 + 2;                             // ints in sort_sums
@@ -181,5 +216,8 @@ extern "C" int tef_cm_sizes(const tef_cm_desc *d, int linear, long *out) {
     out[8] = p.ig.Wp;
     out[9] = p.nchunks;                                           // partial sums per image: acc_sum / acc_nnz hold F*B*slots*nchunks entries
     out[10] = p.det ? (long)p.F * p.B * p.nslots * 4 * p.ig.plane * 2 : 0;   // floats in gimg (deterministic mode)
+    const bool quad_ok = !linear && !p.det;
+    out[11] = quad_ok ? (long)p.F * p.B * p.nslots * 2 * 4 * p.res.cplane * 8 : 0;   // floats in gimgq
+    out[12] = quad_ok ? (long)p.F * p.P * p.B * 4 * p.res.cplane * 8 : 0;            // floats in flowq
     return 0;
 }

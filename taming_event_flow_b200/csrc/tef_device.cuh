@@ -19,11 +19,13 @@ struct Res {
     float sh, sw;     // (H-1)/2, (W-1)/2  (ATen's align_corners=True scaling factor)
     float rhm1, rwm1; // RN(1/hm1), RN(1/wm1) for div_const()
     int Wp, fplane;   // packed flow maps: padded row length (even, >= W+2) and plane size (H+1)*Wp, see sample_flow()
+    int CX, cplane;   // quad-cell copies (flow maps, gradient images): cells per row W/2+1 and per phase plane (H/2+1)*CX, see quad_cell()
     float2 m1_xy, rm1_xy, s_xy;   // the same constants as (x, y) pairs for the packed fp32x2 path: (wm1, hm1), (rwm1, rhm1), (sw, sh)
     __host__ __device__ static Res make(int H, int W) {
         Res r; r.H = H; r.W = W; r.hm1 = (float)(H - 1); r.wm1 = (float)(W - 1);
         r.sh = r.hm1 / 2.0f; r.sw = r.wm1 / 2.0f; r.rhm1 = 1.0f / r.hm1; r.rwm1 = 1.0f / r.wm1;
         r.Wp = (W + 3) & ~1; r.fplane = (H + 1) * r.Wp;
+        r.CX = W / 2 + 1; r.cplane = (H / 2 + 1) * r.CX;
         r.m1_xy.x = r.wm1; r.m1_xy.y = r.hm1; r.rm1_xy.x = r.rwm1; r.rm1_xy.y = r.rhm1; r.s_xy.x = r.sw; r.s_xy.y = r.sh;
         return r;
     }
@@ -119,6 +121,21 @@ __device__ __forceinline__ const float4 *tap_row(const float2 *__restrict__ map,
     return reinterpret_cast<const float4 *>(map + (phase * r.fplane + y * r.Wp + x0 + phase));
 }
 
+// Quad-cell copy of a map (DESIGN.md decision 15).  The 2x2 neighbourhood (y0..y0+1) x (x0..x0+1) of an in-image position is
+// ONE 32-byte record: the map is stored four times, once per parity (x0 & 1, y0 & 1), as rows of cells
+// {row y0: (left, right), row y0+1: (left, right)} of float2 pixels, zero where the pixel lies outside the map.  A bilinear
+// sample (or the corner quad of a gradient image) is then a single 256-bit gather touching one sector, where the dual-phase
+// rows need two 16-byte gathers in two sectors.  Layout per map: [py*2+px][H/2+1][W/2+1] cells of 2 float4.
+__device__ __forceinline__ int quad_cell(const Res &r, int y0, int x0) {
+    const int px = x0 & 1, py = y0 & 1;
+    return (py * 2 + px) * r.cplane + ((y0 + py) >> 1) * r.CX + ((x0 + px) >> 1);
+}
+__device__ __forceinline__ void load_quad(const float4 *__restrict__ cells, int cell, float4 &top, float4 &bot) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(top.x), "=f"(top.y), "=f"(top.z), "=f"(top.w), "=f"(bot.x), "=f"(bot.y), "=f"(bot.z), "=f"(bot.w)
+                 : "l"(cells + 2 * (long)cell));
+}
+
 template <bool KEEP>
 __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
     Bil b;
@@ -149,7 +166,9 @@ __device__ __forceinline__ float2 sample_flow(const float2 *__restrict__ map, co
 // div_const()'s guard becomes: exact division only for a non-zero numerator below 1e-30; a zero numerator may take
 // the corrected product, which returns +0 where a / c returns the numerator's signed zero -- the "- 1.0f" that
 // follows gives -1 either way.
-template <bool KEEP>
+// QUAD: `map` points at the quad-cell copy of the map (float4 cells) instead of the dual-phase rows: same eight values from one
+// 256-bit gather.
+template <bool KEEP, bool QUAD = false>
 __device__ __forceinline__ float2 sample_flow_inside_xy(const float2 *__restrict__ map, const Res &r, float2 p /* (x, y) */, Taps *tp) {
     const float2 a = add2(p, p);                                   // 2.0f * v (exact either way)
     float2 g;
@@ -166,13 +185,13 @@ __device__ __forceinline__ float2 sample_flow_inside_xy(const float2 *__restrict
     const float2 fr = sub2(i, fl);                                 // (w_, n_)
     const float2 om = sub2(bc(1.0f), fr);                          // (e_, s_)
     const int x0 = (int)fl.x, y0 = (int)fl.y;
-    const float4 *q = tap_row(map, r, y0, x0);
-#ifdef TEF_EXP_NO_GATHER
-    const float4 top = make_float4(0.3f * (float)(x0 & 7), -0.2f, 0.1f, 0.4f), bot = make_float4(0.2f, 0.1f * (float)(y0 & 3), -0.3f, 0.2f);
-    if (q == nullptr) return make_float2(0.f, 0.f);
-#else
-    const float4 top = __ldg(q), bot = __ldg(q + (r.Wp >> 1));
-#endif
+    float4 top, bot;
+    if (QUAD) {
+        load_quad(reinterpret_cast<const float4 *>(map), quad_cell(r, y0, x0), top, bot);
+    } else {
+        const float4 *q = tap_row(map, r, y0, x0);
+        top = __ldg(q); bot = __ldg(q + (r.Wp >> 1));
+    }
     const float2 ew = make_float2(om.x, fr.x);                     // (e_, w_)
     const float2 w01 = mul2(bc(om.y), ew);                         // s_*e_, s_*w_
     const float2 w23 = mul2(bc(fr.y), ew);                         // n_*e_, n_*w_
@@ -190,9 +209,9 @@ __device__ __forceinline__ float2 sample_flow_inside_xy(const float2 *__restrict
     }
     return o;
 }
-template <bool KEEP>
+template <bool KEEP, bool QUAD = false>
 __device__ __forceinline__ float2 sample_flow_inside(const float2 *__restrict__ map, const Res &r, float y, float x, Taps *tp) {
-    return sample_flow_inside_xy<KEEP>(map, r, make_float2(x, y), tp);
+    return sample_flow_inside_xy<KEEP, QUAD>(map, r, make_float2(x, y), tp);
 }
 
 // get_event_flow (utils/iwe.py:17-40) of one location (y, x) on planar maps [H][W]: ATen's bilinear grid_sample

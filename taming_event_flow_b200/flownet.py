@@ -80,9 +80,11 @@ class RecEVFlowNet(nn.Module):
             if pred is not None:
                 x = torch.cat([pred, x], 1)
             x = torch.relu(self.dec[i](F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)))
-            pred = torch.tanh(self.heads[i](x))
-            up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
-            flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
+            # the flow heads stay fp32 under autocast: a bf16 tanh would quantise the flow (x 32 px) to ~0.1 px
+            with torch.autocast(x.device.type, enabled=False):
+                pred = torch.tanh(self.heads[i](x.float()))
+                up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
+                flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
         return {"flow": flows}
 
 

@@ -23,6 +23,8 @@ _MODES = {"one": 1, "two": 2, "four": 4}
 
 # TEF_FUSED_HIST=0: build the tile-sort histogram inside the forward call instead of inside update() (A/B switch)
 _FUSED_HIST = os.environ.get("TEF_FUSED_HIST", "1") != "0"
+# TEF_QUAD=0: no quad-cell copies of the flow maps and gradient images (A/B switch; DESIGN.md decision 15)
+_QUAD = os.environ.get("TEF_QUAD", "1") != "0"
 
 
 class _Workspace:
@@ -60,7 +62,8 @@ class _Window:
         self.pool = pool       # the module's list of idle workspaces
         self.ws = pool.pop() if pool else _Workspace()
         self.flows = []        # flows[t][f]: the caller's tensors (autograd leaves of the loss)
-        self.packed = None     # [F,P,B,H,W,2]
+        self.packed = None     # [F,P,B,2,H+1,Wp,2] dual-phase rows
+        self.packedq = None    # [F,P,B,4,H/2+1,W/2+1,8] quad cells (Iterative, non-deterministic) or None
         self.ev = ([], [])     # device addresses of the staged event rows per pass, (grad set, detached set)
         self.mk = ([], [])
         self.n = ([], [])
@@ -142,7 +145,7 @@ class _Smoothness(torch.autograd.Function):
                   "tef_flow_temporal_smoothing_bwd")
         else:
             check(L.tef_flow_spatial_smoothing_bwd(ptr(w.packed), ptr(g), ptr(gpacked), B, H, W, P, F, n, stream()), "tef_flow_spatial_smoothing_bwd")
-        check(L.tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, 0, stream()), "tef_unpack_flow_grad")
+        check(L.tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, 0, None, stream()), "tef_unpack_flow_grad")
         out = [grads[t, f] if t < n else None for t in range(len(w.flows)) for f in range(F)]
         return (None, None, None, None) + tuple(out)
 
@@ -217,6 +220,8 @@ class BaseEventWarping(torch.nn.Module):
             w.shape = (F, B, H, W)
             Wp = (W + 3) & ~1                      # dual-phase, zero-padded maps (csrc/tef_device.cuh)
             w.packed = w.ws.get("packed", (F, self._max_passes(), B, 2, H + 1, Wp, 2), torch.float32, f0.device)
+            if _QUAD and not self._linear and not self.deterministic:
+                w.packedq = w.ws.get("packedq", (F, self._max_passes(), B, 4, H // 2 + 1, W // 2 + 1, 8), torch.float32, f0.device)
         w.flows.append(list(flow_list))
 
     def _update_pass(self, flow_list, event_list, pol_mask, d_event_list, d_pol_mask):
@@ -236,6 +241,8 @@ class BaseEventWarping(torch.nn.Module):
                 keep.append(fl)
             u.flow_maps[f] = fl.data_ptr()
         u.packed = w.packed.data_ptr()
+        if w.packedq is not None:
+            u.packedq = w.packedq.data_ptr()
         round_ts = self.config["loss"]["round_ts"]
         dev = w.packed.device
         for k, (ev, mk) in enumerate(((event_list, pol_mask), (d_event_list, d_pol_mask))):
@@ -307,15 +314,17 @@ class BaseEventWarping(torch.nn.Module):
                 d.mk[k][t] = w.mk[k][t]
                 d.n[k][t] = w.n[k][t]
         d.flow = w.packed.data_ptr()
+        if w.packedq is not None:
+            d.flowq = w.packedq.data_ptr()
         d.hist_done = int(w.hist_valid)
         return d
 
     def _forward_kernels(self, w):
         F, B, H, W = w.shape
         d = self._desc(w)
-        sz = (ctypes.c_long * 11)()
+        sz = (ctypes.c_long * 13)()
         check(lib().tef_cm_sizes(ctypes.byref(d), int(self._linear), sz), "tef_cm_sizes")
-        nslots, n_img, w.n_gflow, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp, nchunks, n_gimg = (int(v) for v in sz)
+        nslots, n_img, w.n_gflow, n_bins, n_sums, rows, rows_grad, n_pos, w.Wp, nchunks, n_gimg, w.n_gimgq, _ = (int(v) for v in sz)
         dev = w.packed.device
         i32, f32 = torch.int32, torch.float32
         if w.ws is None:
@@ -327,7 +336,7 @@ class BaseEventWarping(torch.nn.Module):
         w.gimg = g("gimg", (max(n_gimg, 1),), f32, dev)
         w.acc_sum = g("acc_sum", (F, B, nslots, nchunks), torch.float64, dev)
         w.acc_nnz = g("acc_nnz", (F, B, nslots, nchunks), i32, dev)
-        w.den = g("den", (F, B, nslots), f32, dev)
+        w.den = g("den", (F * B * nslots + 2,), f32, dev)            # + scale, 1/scale of the deterministic gradient words
         w.nslots = nslots
         loss = torch.empty((1,), dtype=f32, device=dev)
         self._fill_workspace(d, w)
@@ -353,13 +362,16 @@ class BaseEventWarping(torch.nn.Module):
         d = w.desc if w.desc is not None else self._desc(w)          # the descriptor of the forward call (same workspace)
         dev = w.packed.device
         gpacked = w.ws.get("gpacked", (w.n_gflow,), torch.float32, dev)
+        if w.packedq is not None and w.n_gimgq > 0:
+            d.gimgq = w.ws.get("gimgq", (w.n_gimgq,), torch.float32, dev).data_ptr()
         grads = torch.empty((P, F, B, 2, H, W), dtype=torch.float32, device=dev)     # handed to autograd: not pooled
         g = gout.detach().float().contiguous().reshape(1)
         self._fill_workspace(d, w)
         d.gflow, d.grad_out = gpacked.data_ptr(), g.data_ptr()
         fn = lib().tef_linear_backward if self._linear else lib().tef_iterative_backward
         check(fn(ctypes.byref(d), stream()), "tef_linear_backward" if self._linear else "tef_iterative_backward")
-        check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, int(self.deterministic), stream()), "tef_unpack_flow_grad")
+        det_scale = ctypes.c_void_p(w.den.data_ptr() + 4 * F * B * w.nslots) if self.deterministic else None
+        check(lib().tef_unpack_flow_grad(ptr(gpacked), ptr(grads), F, P, B, H, W, int(self.deterministic), det_scale, stream()), "tef_unpack_flow_grad")
         w.consumed = True
         w.release()                # stream order makes reuse by the next window safe
         return grads
@@ -371,9 +383,10 @@ class BaseEventWarping(torch.nn.Module):
         if w.img is None or w.consumed:
             raise RuntimeError("images() is only available between forward() and backward()")
         F, B, H, W = w.shape
-        if self.deterministic:                                        # int64 fixed point, 2^-40
-            v = w.img.view(torch.int64).view(F, B, w.nslots, 2, 2, H, w.Wp, 2)
-            s = ((v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]).double() * 2.0 ** -40).float()
+        if self.deterministic:                                        # int64 fixed point: high words (2^-40), then low words (2^-88)
+            v = w.img.view(torch.int64).view(2, F, B, w.nslots, 2, 2, H, w.Wp, 2)
+            v = v[:, :, :, :, 0, :, :, 0:W, :] + v[:, :, :, :, 1, :, :, 1:W + 1, :]
+            s = (v[0].double() * 2.0 ** -40 + v[1].double() * 2.0 ** -88).float()
         else:
             v = w.img.view(F, B, w.nslots, 2, 2, H, w.Wp, 2)          # [.., phase, pol, H, Wp, (count, tw)]
             s = v[:, :, :, 0, :, :, 0:W, :] + v[:, :, :, 1, :, :, 1:W + 1, :]

@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 def test_descriptor_layout_matches_header():
     from taming_event_flow_b200 import _lib
 
-    # 10 ints, then 2x31 pointers x2, 2x31 ints, 14 pointers
-    expect = 10 * 4 + 2 * 31 * 8 * 2 + 2 * 31 * 4 + 14 * 8 + 2 * 4
+    # 10 ints, then 2x31 pointers x2, 2x31 ints, 14 pointers, 2 ints, 2 pointers
+    expect = 10 * 4 + 2 * 31 * 8 * 2 + 2 * 31 * 4 + 14 * 8 + 2 * 4 + 2 * 8
     assert ctypes.sizeof(_lib.CmDesc) == expect
     lib = ctypes.CDLL(_lib.LIB_PATH)
     d = _lib.CmDesc()
@@ -94,7 +94,9 @@ def test_no_contracted_packed_multiply_adds_in_the_event_kernels():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     _lib.build()
-    expect = {"iter_fwd_kernelILb0E": 10, "iter_fwd_kernelILb1E": 10, "iter_bwd_kernelILb0E": 4, "iter_bwd_kernelILb1E": 4}
+    # <deterministic, quad-cell copies>: every instantiation has the same per-event arithmetic
+    expect = {"iter_fwd_kernelILb0ELb0E": 10, "iter_fwd_kernelILb0ELb1E": 10, "iter_fwd_kernelILb1ELb0E": 10,
+              "iter_bwd_kernelILb0ELb0E": 4, "iter_bwd_kernelILb0ELb1E": 4, "iter_bwd_kernelILb1ELb0E": 4}
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     counts, cur = {}, None
     for line in sass.splitlines():

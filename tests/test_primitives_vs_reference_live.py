@@ -101,5 +101,21 @@ def test_reference_encoding_error_and_last_writer_behaviour():
     for bad_x, bad_y in ((20.0, 0.0), (0.0, 12.0), (-21.0, 0.0), (0.0, -13.0)):
         with pytest.raises(IndexError):
             ref_enc.events_to_image(torch.tensor([bad_x]), torch.tensor([bad_y]), torch.tensor([1.0]), sensor_size=(12, 20))
+        for fn in (orc.events_to_image, orc.events_to_channels):
+            with pytest.raises(IndexError):
+                fn(np.float32([bad_x]), np.float32([bad_y]), np.float32([1.0]), (12, 20))
+        with pytest.raises(IndexError):
+            orc.events_to_voxel(np.float32([bad_x]), np.float32([bad_y]), np.float32([0.5]), np.float32([1.0]), 3, (12, 20))
     img = ref_enc.events_to_image(torch.tensor([-1.0, 3, 3]), torch.tensor([-12.0, 1, 1]), torch.tensor([1.0, 2, 5]), sensor_size=(12, 20), accumulate=False)
     assert img[0, 19] == 1.0 and img[1, 3] == 5.0
+    # the oracle follows: negative coordinates wrap, accumulate=False keeps the last event of a pixel
+    r = np.random.default_rng(5)
+    n, H, W = 500, 12, 20
+    xs = r.integers(-W, W, n).astype(np.float32)
+    ys = r.integers(-H, H, n).astype(np.float32)
+    ts = np.sort(r.random(n)).astype(np.float32)
+    ps = r.normal(size=n).astype(np.float32)
+    for acc in (True, False):
+        assert same(ref_enc.events_to_image(T(xs), T(ys), T(ps), sensor_size=(H, W), accumulate=acc), orc.events_to_image(xs, ys, ps, (H, W), accumulate=acc))
+    assert same(ref_enc.events_to_channels(T(xs), T(ys), T(ps), sensor_size=(H, W)), orc.events_to_channels(xs, ys, ps, (H, W)))
+    assert same(ref_enc.events_to_voxel(T(xs), T(ys), T(ts), T(ps), 4, sensor_size=(H, W)), orc.events_to_voxel(xs, ys, ts, ps, 4, (H, W)))
