@@ -170,6 +170,67 @@ def run_cpu_baseline(wl, repeats=2):
     }
 
 
+def reference_root():
+    """Where the UNMODIFIED reference can be imported from: the build container mounts it at /root/reference; a pip --target
+    install would sit in baseline/_ref.  Neither exists on the GPU box (the reference is plain Python without a setup.py, so
+    there is nothing to install), and then the stock arms below are reported as unavailable."""
+    for cand in (os.environ.get("TEF_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.exists(os.path.join(cand, "loss", "flow.py")):
+            return cand
+    return None
+
+
+def stock_reference_step(ref_mods, wl, seq, device):
+    """One loss window through the reference's own classes (upstream loss/flow.py:415-746): update x P, forward, backward."""
+    import copy
+
+    from taming_event_flow_b200 import synthetic as syn
+
+    cfg = syn.loss_config(wl["H"], wl["W"], wl["B"], wl["P"], wl["S"], wl["mode"], warping=wl["warping"])
+    m = getattr(ref_mods, wl["warping"])(copy.deepcopy(cfg), device)
+    flows = [[f.to(device).clone().requires_grad_(True) for f in per] for per in seq["flows"]]
+    t0 = time.perf_counter()
+    for t in range(wl["P"]):
+        m.update(flows[t], seq["events"][t].to(device).clone(), seq["masks"][t].to(device).clone(), seq["d_events"][t].to(device).clone(),
+                 seq["d_masks"][t].to(device).clone())
+    loss = m()
+    loss.backward()
+    if device != "cpu":
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, float(loss.item())
+
+
+def run_stock_reference(wl, n, repeats=1):
+    """The reference itself (not the port), on the host cores and -- when a GPU is visible -- on CUDA in eager mode
+    (SURVEY.md 8d last row).  Returns None where the reference cannot be imported."""
+    root = reference_root()
+    if root is None:
+        return None
+    import importlib
+
+    sys.path.insert(0, root)
+    try:
+        ref_mods = importlib.import_module("loss.flow")
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:160]}
+    finally:
+        sys.path.remove(root)
+    seq = fast_sequence(1234, wl, n_override=n)
+    ev = events_per_step(wl, n)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    out = {"source": root, "events_per_window": n, "events_per_step": ev}
+    for device in ["cpu"] + (["cuda"] if torch.cuda.is_available() else []):
+        stock_reference_step(ref_mods, wl, seq, device)             # warm-up
+        best = min(stock_reference_step(ref_mods, wl, seq, device)[0] for _ in range(repeats))
+        out[device] = {"value": ev / best / 1e6, "unit": "Mevents/s", "s_per_step": best, "threads": threads if device == "cpu" else None,
+                       "note": "unmodified reference classes, eager PyTorch %s" % torch.__version__}
+    return out
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -190,13 +251,25 @@ def run_reference_arm(args, wl):
     v = ev * args.steps / dt / 1e6
     sample = "%s with %d events/window (%d events/step), CPU port of the reference algorithm (oracle/cm_oracle.c), OpenMP on %d threads" % (
         wl["name"], n, ev, threads)
+    # the reference itself, where it can be imported (build container): a smaller sample, it is ~10x slower than the port
+    stock = None
+    if os.environ.get("TEF_STOCK_REFERENCE", "1") != "0":
+        try:
+            stock = run_stock_reference(wl, min(n, 50_000 if wl["H"] * wl["W"] > 128 * 128 else n))
+        except Exception as exc:
+            stock = {"unavailable": repr(exc)[:160]}
+    cfg = workload_config(wl)
+    cfg["events_per_window"] = n                       # what this arm actually times: a bounded sample of the workload (a rate, so the ratio holds)
+    cfg["events_per_window_of_workload"] = wl["N"]
     line = {
         "impl": "reference", "metric": "cm_loss_fwd_bwd_throughput", "value": v, "unit": "Mevents/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(wl),
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": "Mevents/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "stock_reference": stock if stock is not None else {"unavailable": "the reference sources are not on this machine (/root/reference exists in the build container only; "
+                                                                            "it is plain Python without a setup.py, so nothing can be pip-installed into baseline/_ref)"},
     }
     print(json.dumps(line))
 
@@ -208,6 +281,12 @@ def workload_config(wl):
         "flow_scales": wl["F"], "scales_loss": wl["S"], "event_distribution": wl["dist"], "flow_sigma_px": wl["sigma"],
         "cache": "inputs_larger_than_L2 (fresh event tensors every step)", "ragged": bool(wl.get("ragged", False)),
     }
+
+
+def with_affinity(cfg, affinity):
+    cfg = dict(cfg)
+    cfg["cpu_affinity"] = affinity
+    return cfg
 
 
 # ----------------------------------------------------------------------------------------------
@@ -261,6 +340,25 @@ class ClockSampler:
             mx = None
         sm = [r[0] for r in self.rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (its NUMA node) BEFORE any pinned host memory is
+    allocated, so that the staging buffers of the end-to-end arms live next to the GPU's PCIe root.  Returns a description."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and w * 64 + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return "%d CPUs local to GPU %d (of %d allowed)" % (len(cpus), index, len(allowed))
+    except Exception as exc:
+        return "unchanged (%s)" % type(exc).__name__
 
 
 # ----------------------------------------------------------------------------------------------
@@ -330,6 +428,7 @@ def run_ours(args, wl):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
@@ -437,19 +536,27 @@ def run_ours(args, wl):
     main_stream = torch.cuda.current_stream(dev)
     e2e_steps = max(3, min(args.steps, 10))
 
-    def run_pipeline(host_tensors, windows_of):
-        """host_tensors: pinned inputs of one step, [0] = all flow maps; windows_of(slot, t) -> the four event tensors.
+    def run_pipeline(host_tensors, windows_of, full):
+        """host_tensors: pinned inputs of one step; windows_of(slot, t) -> the four event tensors of pass t.
+        full = True: the flow maps are inputs too (host_tensors[0], uploaded every step) and every flow gradient is read back;
+        full = False: the step a training loop runs -- only the EVENTS cross PCIe, the flow maps are device tensors (a network's
+        output), their gradients stay on the device (the network's backward consumes them) and the loss is read back.
         Two device slots are allocated once (a prefetching loader's staging buffers): no allocator traffic when timed."""
         slots = [tuple(torch.empty_like(h, device=dev) for h in host_tensors) for _ in range(2)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
         read_back = torch.cuda.Event()
+        copy_marks = []
 
         def prefetch(k):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[k])      # the step that used this slot has finished with it
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record(copy_stream)
                 for d, h in zip(slots[k], host_tensors):
                     d.copy_(h, non_blocking=True)
+                m1.record(copy_stream)
+                copy_marks.append((m0, m1))
                 ready[k].record(copy_stream)
 
         def step(i, last):
@@ -457,24 +564,29 @@ def run_ours(args, wl):
             if not last:
                 prefetch((i + 1) % 2)
             main_stream.wait_event(ready[k])
-            fl_all = slots[k][0]
             module.reset()
             flows = []
             for t in range(P):
-                fl = [fl_all[t, f].requires_grad_(True) for f in range(F)]
+                fl = [slots[k][0][t, f].requires_grad_(True) for f in range(F)] if full else d_flows[t]
                 flows.append(fl)
                 module.update(fl, *windows_of(slots[k], t))
             consumed[k].record(main_stream)              # update() has staged the events and packed the flow maps
             loss = module()
             loss.backward()
             main_stream.wait_event(read_back)            # the previous step's read-back has left d_grads / d_loss
-            torch.stack([f.grad for per in flows for f in per], out=d_grads.view(P * F, B, 2, H, W))
+            if full:
+                torch.stack([f.grad for per in flows for f in per], out=d_grads.view(P * F, B, 2, H, W))
+            else:
+                for per in flows:
+                    for f in per:
+                        f.grad = None
             d_loss.copy_(loss.detach())
             done = torch.cuda.Event()
             done.record(main_stream)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
-                h_grads.copy_(d_grads, non_blocking=True)
+                if full:
+                    h_grads.copy_(d_grads, non_blocking=True)
                 h_loss.copy_(d_loss, non_blocking=True)
                 read_back.record(d2h_stream)
 
@@ -486,6 +598,7 @@ def run_ours(args, wl):
             step(i, False)
         barrier()
         loss_seen = float(h_loss.item())
+        del copy_marks[:]
         # restart the pipeline so that the first timed step pays its own (un-overlapped) upload
         e0.record()
         prefetch(0)
@@ -494,15 +607,17 @@ def run_ours(args, wl):
         main_stream.wait_stream(d2h_stream)              # the last read-back is inside the timed region
         e1.record()
         barrier()
-        return e0.elapsed_time(e1), loss_seen
+        copy_ms = sum(a.elapsed_time(b) for a, b in copy_marks) / max(len(copy_marks), 1)
+        return e0.elapsed_time(e1), loss_seen, copy_ms
 
-    # (1) the reference's own tensors: fp32 event lists + polarity masks, 24 B per event
+    # (1) everything from the host, in the reference's own tensors: fp32 event lists + polarity masks (24 B per event) and the
+    # flow maps up, every flow gradient down
     lists = (h_flow_all, h_ev_all, h_mk_all, h_dev_all, h_dmk_all)
-    h2d = sum(x.numel() * 4 for x in lists)
-    ms_e2e, loss_e2e = run_pipeline(lists, lambda sl, t: (sl[1][t], sl[2][t], sl[3][t], sl[4][t]))
+    h2d_full = sum(x.numel() * 4 for x in lists)
+    ms_full, loss_full, cp_full = run_pipeline(lists, lambda sl, t: (sl[1][t], sl[2][t], sl[3][t], sl[4][t]), True)
     torch.cuda.empty_cache()
 
-    # (2) the packed loader contract: events cross PCIe once, 8 B each, and are formatted (and split into
+    # the packed loader contract: events cross PCIe once, 8 B each, and are formatted (and split into
     # gradient / detached lists) on the device by dataloader/base.py format_windows
     batches = []
     for t in range(P):
@@ -512,23 +627,32 @@ def run_ours(args, wl):
             wins.append(tef_base.pack_events(ev[:, 2].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 0], (ev[:, 3] > 0).astype(np.int64)))
         batches.append(tef_base.PackedBatch(wins))
     k_grad = wl["N"] if wl["Nd"] > 0 else None
-    h2d_packed = h_flow_all.numel() * 4 + sum(bt.nbytes for bt in batches)
+    packed_bytes = sum(bt.nbytes for bt in batches)
 
+    def packed_windows(off):
+        def fn(sl, t):
+            w = tef_base.format_windows(batches[t], (H, W), dev, max_num_grad_events=k_grad, with_cnt=False, uploaded=(sl[off + 2 * t], sl[off + 1 + 2 * t]))
+            return w["event_list"], w["event_list_pol_mask"], w["d_event_list"], w["d_event_list_pol_mask"]
+        return fn
+
+    # (2) packed events + flow maps up, gradients down
     packed_host = [h_flow_all]
     for bt in batches:
         packed_host.extend([bt.host, bt.offsets_host])
+    ms_packed_full, loss_packed_full, cp_packed_full = run_pipeline(tuple(packed_host), packed_windows(1), True)
+    torch.cuda.empty_cache()
 
-    def packed_windows(sl, t):
-        w = tef_base.format_windows(batches[t], (H, W), dev, max_num_grad_events=k_grad, with_cnt=False, uploaded=(sl[1 + 2 * t], sl[2 + 2 * t]))
-        return w["event_list"], w["event_list_pol_mask"], w["d_event_list"], w["d_event_list_pol_mask"]
-
-    ms_packed, loss_packed = run_pipeline(tuple(packed_host), packed_windows)
+    # (3) THE HEADLINE e2e: what crosses PCIe in a training step -- the packed events up, the loss down; flow maps and their
+    # gradients are device tensors on both sides of the loss (network output / network backward)
+    ms_e2e, loss_e2e, cp_e2e = run_pipeline(tuple(packed_host[1:]), packed_windows(0), False)
+    h2d, d2h_e2e = packed_bytes, 4
 
     # ---- aggregate over ranks (max time), whole-job throughput
-    times = torch.tensor([ms, ms_e2e, ms_packed], dtype=torch.float64, device=dev)
+    # ---- aggregate over ranks (max time), whole-job throughput
+    times = torch.tensor([ms, ms_e2e, ms_packed_full, ms_full, cp_e2e, cp_packed_full, cp_full], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_packed = times.tolist()
+    ms, ms_e2e, ms_packed_full, ms_full, cp_e2e, cp_packed_full, cp_full = times.tolist()
     value = world * E * args.steps / (ms * 1e-3) / 1e6
     e2e_value = world * E * e2e_steps / (ms_e2e * 1e-3) / 1e6
 
@@ -582,12 +706,19 @@ def run_ours(args, wl):
         line = {
             "metric": "cm_loss_fwd_bwd_throughput", "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl), "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": ms_e2e / e2e_steps, "loss": loss_e2e},
-            "e2e_packed": {"value": world * E * e2e_steps / (ms_packed * 1e-3) / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": h2d_packed,
-                           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_packed / e2e_steps, "loss": loss_packed,
-                           "note": "events uploaded as 8-byte packed records and formatted on the device (dataloader/base.py format_windows)"},
+            "config": with_affinity(workload_config(wl), affinity), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_e2e, "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps, "loss": loss_e2e, "h2d_gbps_per_gpu_while_copying": round(h2d / (cp_e2e * 1e-3) / 1e9, 2),
+                    "note": "what crosses PCIe in a training step: events uploaded from pinned host memory as 8-byte packed records (dataloader/base.py "
+                            "pack_events / format_windows) and the loss read back; flow maps and flow gradients are device tensors (network output / network "
+                            "backward).  e2e_full_* upload the flow maps and read every gradient back as well"},
+            "e2e_full_packed": {"value": world * E * e2e_steps / (ms_packed_full * 1e-3) / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": h_flow_all.numel() * 4 + packed_bytes,
+                                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_packed_full / e2e_steps, "loss": loss_packed_full,
+                                "h2d_gbps_per_gpu_while_copying": round((h_flow_all.numel() * 4 + packed_bytes) / (cp_packed_full * 1e-3) / 1e9, 2)},
+            "e2e_full_fp32_lists": {"value": world * E * e2e_steps / (ms_full * 1e-3) / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h,
+                                    "steps": e2e_steps, "ms_per_step": ms_full / e2e_steps, "loss": loss_full,
+                                    "h2d_gbps_per_gpu_while_copying": round(h2d_full / (cp_full * 1e-3) / 1e9, 2),
+                                    "note": "round 1's e2e: the reference's own fp32 tensors (24 B per event) and the flow maps up, all gradients down"},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "cpu_baseline": cpu,
             "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"], "share_of_step": round(v["ms_total"] / prof_steps / ms_prof, 4)}
                         for k, v in kern.items()},

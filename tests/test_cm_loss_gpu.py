@@ -594,3 +594,29 @@ def test_smoothness_beyond_the_loss_window_is_refused():
         m.update([f.cuda() for f in seq["flows"][t]], seq["events"][t].cuda(), seq["masks"][t].cuda(), seq["d_events"][t].cuda(), seq["d_masks"][t].cuda())
     with pytest.raises(NotImplementedError):
         m()
+
+
+def test_quad_cell_copies_give_the_same_results(monkeypatch):
+    """TEF_QUAD=1 routes the chain steps and the gradient-image gathers through the quad-cell copies (one 256-bit gather per
+    2x2 neighbourhood, csrc/tef_device.cuh quad_cell).  Same eight values per fetch, so the deterministic-order parts must
+    agree exactly: sparse (non-overlapping) events give bit-identical images, and loss / gradients agree to summation order."""
+    from taming_event_flow_b200.loss import flow as tef_flow
+
+    B, P, N, Nd, H, W, F = 3, 6, 3000, 1000, 47, 62, 2                 # odd sizes: the last cell row / column is half outside
+    seq = syn.make_sequence(19, B, P, N, Nd, H, W, F, 3.0, True, "uniform")
+    for t in range(P):                                                  # a few events beyond the sensor: the generic first step
+        seq["events"][t][:, :5, 1] = H + 2.0
+        seq["events"][t][:, 5:9, 2] = -3.0
+    cfg = syn.loss_config(H, W, B, P, 1, "two")
+    out = {}
+    for quad in (False, True):
+        monkeypatch.setattr(tef_flow, "_QUAD", quad)
+        out[quad] = _run_gpu("iterative", cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
+        assert (out[quad]["module"]._win.packedq is not None) == quad or out[quad]["module"]._win.ws is None
+    assert abs(out[True]["loss"] - out[False]["loss"]) <= 1e-6 * abs(out[False]["loss"])
+    assert np.array_equal(out[True]["iwe"] != 0, out[False]["iwe"] != 0)
+    assert rel_err(out[True]["iwe"], out[False]["iwe"])[0] < 1e-6
+    assert rel_err(out[True]["gflow"], out[False]["gflow"])[0] < 1e-6
+    oc = orc.make_cfg(B, H, W, P, F, 1, "two", True)
+    o = orc.iterative(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], np.float32, want_grad=True, want_iwe=True)
+    assert rel_err(out[True]["gflow"], o["gflow"])[0] < TOL and rel_err(out[True]["iwe"], o["iwe"])[0] < TOL
