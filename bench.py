@@ -399,6 +399,40 @@ def measure_l2_rates(L, dev):
     return out
 
 
+def encoding_roofline(L, dev, hbm, N=1_000_000, H=480, W=640, bins=5, reps=20):
+    """HBM roofline of the event encodings (dataloader/encodings.py) on one DSEC-resolution window: kernel-only times from the
+    library's CUDA events.  Algorithmic bytes: events_to_voxel 16 N + 4 bins H W, events_to_channels 12 N + 8 H W."""
+    import ctypes
+
+    from taming_event_flow_b200.dataloader import encodings as enc
+
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randint(0, W, (N,), generator=g).float().to(dev)
+    ys = torch.randint(0, H, (N,), generator=g).float().to(dev)
+    ts = torch.sort(torch.rand(N, generator=g))[0].to(dev)
+    ps = (torch.randint(0, 2, (N,), generator=g) * 2 - 1).float().to(dev)
+    L.tef_prof_name.restype = ctypes.c_char_p
+    kid = [k for k in range(L.tef_prof_num_kernels()) if L.tef_prof_name(k) == b"encoding_kernels"][0]
+    out = {}
+    for name, call, nbytes in (("to_voxel_kernel", lambda: enc.events_to_voxel(xs, ys, ts, ps, bins, (H, W)), 16 * N + 4 * bins * H * W),
+                               ("to_channels_kernel", lambda: enc.events_to_channels(xs, ys, ps, (H, W)), 12 * N + 8 * H * W)):
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        L.tef_prof_reset()
+        L.tef_prof_enable(1)
+        for _ in range(reps):
+            call()
+        torch.cuda.synchronize()
+        L.tef_prof_enable(0)
+        tot, timed, cnt = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+        L.tef_prof_read(kid, ctypes.byref(tot), ctypes.byref(timed), ctypes.byref(cnt))
+        ms = tot.value / max(timed.value, 1)
+        out[name] = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm,
+                     "kernel_ms_avg": ms, "algorithmic_bytes_per_launch": nbytes, "events": N, "resolution": [H, W]}
+    return out
+
+
 def cm_lane_ops(wl, kernel):
     """Lane-op counts of the two Iterative kernels as issued (mode two, S = 1), per event and flow scale: P+1 chain steps of
     two 16-byte tap-row gathers and ~0.8 P reference times of 2 red.v4 (forward); ~0.8 P nodes of 2 + 2 16-byte gathers
@@ -688,6 +722,10 @@ def run_ours(args, wl):
                 l2["kernels"][k] = {"gathers16": int(ops["gathers"]), "red_v4": int(ops["reds"]), "ms_gathers_at_peak": round(t_g * 1e3, 4),
                                     "ms_reds_at_peak": round(t_r * 1e3, 4), "bound": "gather" if t_g >= t_r else "red",
                                     "frac": round(t_min * 1e3 / kern[k]["ms_avg"], 4)}
+        try:
+            enc_roof = encoding_roofline(L, dev, hbm)
+        except Exception as exc:
+            enc_roof = {"error": repr(exc)[:200]}
         cpu = run_cpu_baseline(wl)
     # the second half of BASELINE.json's metric ("train windows/s"): a short run of the training-step workload
     # (PyTorch network + CM loss + SUM all-reduce), reported as an extra key of the same line
@@ -700,6 +738,9 @@ def run_ours(args, wl):
             targs.train_dtype = "bf16"            # same step with the network under bf16 autocast (fp32 flow heads, fp32 CM loss)
             t16 = run_train(targs, dict(TRAIN_WORKLOADS["train_128x128_b8"], name="train_128x128_b8"), quiet=True)
             train["bf16_network"] = {k: t16[k] for k in ("value", "unit", "ms_per_step", "dtype")}
+            targs.fp32_heads = False
+            t16 = run_train(targs, dict(TRAIN_WORKLOADS["train_128x128_b8"], name="train_128x128_b8"), quiet=True)
+            train["bf16_network_bf16_heads"] = {k: t16[k] for k in ("value", "unit", "ms_per_step", "dtype")}
         except Exception as exc:      # the extra must never take the headline number down
             train = {"error": repr(exc)[:200]}
     if rank == 0:
@@ -719,7 +760,7 @@ def run_ours(args, wl):
                                     "steps": e2e_steps, "ms_per_step": ms_full / e2e_steps, "loss": loss_full,
                                     "h2d_gbps_per_gpu_while_copying": round(h2d_full / (cp_full * 1e-3) / 1e9, 2),
                                     "note": "round 1's e2e: the reference's own fp32 tensors (24 B per event) and the flow maps up, all gradients down"},
-            "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "roofline_encodings": enc_roof, "cpu_baseline": cpu,
             "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"], "share_of_step": round(v["ms_total"] / prof_steps / ms_prof, 4)}
                         for k, v in kern.items()},
             "kernels_note": "per-kernel CUDA events in a second pass of %d steps at %.4f ms/step (the events themselves cost the difference to ms_per_step)" % (prof_steps, ms_prof),
@@ -769,7 +810,8 @@ def run_train(args, wl, quiet=False):
     dtype = getattr(args, "train_dtype", None) or os.environ.get("TEF_TRAIN_DTYPE", TRAIN_DTYPE_DEFAULT)
     autocast = torch.bfloat16 if dtype == "bf16" else None
     torch.backends.cudnn.benchmark = True
-    model = RecEVFlowNet(num_bins=2).to(dev).to(memory_format=torch.channels_last)
+    fp32_heads = os.environ.get("TEF_TRAIN_FP32_HEADS", "1") != "0" and getattr(args, "fp32_heads", True)
+    model = RecEVFlowNet(num_bins=2, fp32_heads=fp32_heads).to(dev).to(memory_format=torch.channels_last)
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)      # the optimizer step stays outside the captured graph
     reducer = GradReducer(list(model.parameters()), world)
     from taming_event_flow_b200.dataloader.encodings import events_to_channels_batched
@@ -823,7 +865,7 @@ def run_train(args, wl, quiet=False):
     res = {"metric": "train_throughput", "value": B_global * P * args.steps / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch/cuDNN, channels_last, %s, 31.4M params)" % ("bf16 autocast, fp32 CM loss" if autocast else "fp32/TF32"),
+           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch/cuDNN, channels_last, %s, 31.4M params)" % (("bf16 autocast, %s flow heads, fp32 CM loss" % ("fp32" if fp32_heads else "bf16")) if autocast else "fp32/TF32"),
                           step_mode=("one CUDA graph over forward + CM loss + backward; all-reduce, clip, Adam eager" if mode == "graph" else "eager"),
                           optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets) under the backward pass" % len(reducer.buckets)),
            "loss": float(loss.item()), "events_per_step": B_global * P * (wl["N"] + wl["Nd"])}

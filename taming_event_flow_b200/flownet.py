@@ -44,8 +44,9 @@ class ConvGRUCell(nn.Module):
 
 
 class RecEVFlowNet(nn.Module):
-    def __init__(self, num_bins=2, base_channels=64, num_encoders=4, final_w_scale=0.01):
+    def __init__(self, num_bins=2, base_channels=64, num_encoders=4, final_w_scale=0.01, fp32_heads=True):
         super().__init__()
+        self.fp32_heads = fp32_heads      # under autocast: 1x1 flow heads, tanh and up-sampling in fp32 (bf16 would quantise the flow to 0.4 %)
         chans = [base_channels * 2 ** i for i in range(num_encoders)]            # 64 128 256 512
         ins = [num_bins] + chans[:-1]
         self.enc_conv = nn.ModuleList([_conv(i, o, 3, stride=2) for i, o in zip(ins, chans)])
@@ -80,11 +81,14 @@ class RecEVFlowNet(nn.Module):
             if pred is not None:
                 x = torch.cat([pred, x], 1)
             x = torch.relu(self.dec[i](F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)))
-            # the flow heads stay fp32 under autocast: a bf16 tanh would quantise the flow (x 32 px) to ~0.1 px
-            with torch.autocast(x.device.type, enabled=False):
-                pred = torch.tanh(self.heads[i](x.float()))
+            if self.fp32_heads and torch.is_autocast_enabled(x.device.type):
+                with torch.autocast(x.device.type, enabled=False):
+                    pred = torch.tanh(self.heads[i](x.float()))
+                    up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
+            else:
+                pred = torch.tanh(self.heads[i](x))
                 up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
-                flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
+            flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
         return {"flow": flows}
 
 

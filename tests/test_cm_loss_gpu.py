@@ -612,7 +612,7 @@ def test_quad_cell_copies_give_the_same_results(monkeypatch):
     for quad in (False, True):
         monkeypatch.setattr(tef_flow, "_QUAD", quad)
         out[quad] = _run_gpu("iterative", cfg, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"])
-        assert (out[quad]["module"]._win.packedq is not None) == quad or out[quad]["module"]._win.ws is None
+        assert (out[quad]["module"]._win.packedq is not None) == quad
     assert abs(out[True]["loss"] - out[False]["loss"]) <= 1e-6 * abs(out[False]["loss"])
     assert np.array_equal(out[True]["iwe"] != 0, out[False]["iwe"] != 0)
     assert rel_err(out[True]["iwe"], out[False]["iwe"])[0] < 1e-6
