@@ -244,6 +244,20 @@ int tef_flow_temporal_smoothing_bwd(const float *packed_flow, const float *sums,
 /* loss/flow_val.py -- fused stages of the validation update; */
 /* batch size 1 like upstream; maps are planar [H][W] (x and y flow separately) */
 /* ------------------------------------------------------------------------- */
+/* Everything `update` appends, in one launch (update_base :75-114 and, for Iterative, :483-487, :519-528, :558-562): the window's
+   events [n][4] (ts += pass_index IN PLACE, like upstream) and mask [n][2] are copied to row `offset` of the caller's row arrays
+   (the pointers below already point at that row), the newest flow map [2][H][W] and event mask [H][W] to slot `now` of the
+   per-window stacks (the pointers point at that slot).  ts_override: device scalar for round_ts or NULL.  Linear: fw_* / bw_* /
+   prop_* are NULL. */
+typedef struct tef_val_append {
+    void *events; const void *pol_mask; long n; float pass_index; const float *ts_override;
+    float *ev_ts; float *ev_loc; float *ev_mask;
+    float *fw_ts; float *fw_loc; float *fw_mask;
+    float *bw_loc; float *bw_mask;
+    const float *flow; const float *event_mask; int H, W;
+    float *map_x; float *map_y; float *map_e; float *prop_x; float *prop_y;
+} tef_val_append;
+int tef_val_append_window(const tef_val_append *d, void *stream);
 /* Iterative.update :483-517: every accumulated event one window forward with the newest map, in place:
    loc [n][2] (y, x), ts [n] (set to tref), mask [n][2] */
 int tef_val_forward_step(const float *mapx, const float *mapy, float *loc, float *ts, float *mask, float tref, long n, int H, int W,

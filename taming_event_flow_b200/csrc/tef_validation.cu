@@ -107,6 +107,38 @@ __global__ void __launch_bounds__(kThreads) val_trajectory_kernel(const float *_
     accy[p] = ny - (float)(p / r.W);
 }
 
+// One launch for everything `update` appends (loss/flow_val.py:75-114, :483-487, :519-528, :558-562): CTAs [0, nb_ev) copy the
+// window's events into the row arrays (raw list, forward list, backward list), adding the pass index to the caller's
+// timestamps in place; the other CTAs copy the newest flow map and event mask into the per-window map stacks.
+struct ValAppend {
+    float4 *events; const float2 *mask; long n; float pass_index; const float *ts_override;
+    float *ev_ts; float2 *ev_loc, *ev_mask;                  // raw lists (BaseValidation)
+    float *fw_ts; float2 *fw_loc, *fw_mask;                  // Iterative: forward-warped lists (nullptr for Linear)
+    float2 *bw_loc, *bw_mask;                                // Iterative: this window's rows of the backward-warped lists
+    const float *flow, *emask; long HW;                      // newest flow [2][H][W] and event mask [H][W]
+    float *map_x, *map_y, *map_e, *prop_x, *prop_y;          // slot `now` of the stacks (prop_*: Iterative, else nullptr)
+    int nb_ev;
+};
+__global__ void __launch_bounds__(kThreads) val_append_kernel(const __grid_constant__ ValAppend a) {
+    if ((int)blockIdx.x < a.nb_ev) {
+        const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+        if (i >= a.n) return;
+        float4 e = a.events[i];
+        e.x = e.x + a.pass_index;                            // event_list[:, :, 0:1] += self._passes (in place, :86)
+        a.events[i] = e;
+        const float ts = a.ts_override ? __ldg(a.ts_override) : e.x;      // round_ts (:87-88)
+        const float2 loc = make_float2(e.y, e.z), m = a.mask[i];
+        a.ev_ts[i] = ts; a.ev_loc[i] = loc; a.ev_mask[i] = m;
+        if (a.fw_ts) { a.fw_ts[i] = ts; a.fw_loc[i] = loc; a.fw_mask[i] = m; a.bw_loc[i] = loc; a.bw_mask[i] = m; }
+        return;
+    }
+    const long p = (long)(blockIdx.x - a.nb_ev) * kThreads + threadIdx.x;
+    if (p >= a.HW) return;
+    const float fx = a.flow[p], fy = a.flow[a.HW + p];
+    a.map_x[p] = fx; a.map_y[p] = fy; a.map_e[p] = a.emask[p];
+    if (a.prop_x) { a.prop_x[p] = fx; a.prop_y[p] = fy; }
+}
+
 }  // namespace tef
 
 using namespace tef;
@@ -151,5 +183,23 @@ extern "C" int tef_val_trajectory_step(const float *mapx, const float *mapy, flo
     if (H < 2 || W < 2 || !mapx || !mapy || !idx || !out_mask || !accx || !accy) return TEF_EINVAL;
     ProfScope pr(K_VALIDATION, ST);
     val_trajectory_kernel<<<TEF_GRID((long)H * W), kThreads, 0, ST>>>(mapx, mapy, idx, out_mask, accx, accy, Res::make(H, W));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_val_append_window(const tef_val_append *d, void *stream) {
+    if (!d || d->n < 0 || d->H < 2 || d->W < 2) return TEF_EINVAL;
+    if (!d->flow || !d->event_mask || !d->map_x || !d->map_y || !d->map_e) return TEF_EINVAL;
+    if (d->n > 0 && (!d->events || !d->pol_mask || !d->ev_ts || !d->ev_loc || !d->ev_mask)) return TEF_EINVAL;
+    if (d->fw_ts && (!d->fw_loc || !d->fw_mask || !d->bw_loc || !d->bw_mask || !d->prop_x || !d->prop_y)) return TEF_EINVAL;
+    ValAppend a;
+    a.events = (float4 *)d->events; a.mask = (const float2 *)d->pol_mask; a.n = d->n; a.pass_index = d->pass_index; a.ts_override = d->ts_override;
+    a.ev_ts = d->ev_ts; a.ev_loc = (float2 *)d->ev_loc; a.ev_mask = (float2 *)d->ev_mask;
+    a.fw_ts = d->fw_ts; a.fw_loc = (float2 *)d->fw_loc; a.fw_mask = (float2 *)d->fw_mask;
+    a.bw_loc = (float2 *)d->bw_loc; a.bw_mask = (float2 *)d->bw_mask;
+    a.flow = d->flow; a.emask = d->event_mask; a.HW = (long)d->H * d->W;
+    a.map_x = d->map_x; a.map_y = d->map_y; a.map_e = d->map_e; a.prop_x = d->prop_x; a.prop_y = d->prop_y;
+    a.nb_ev = (int)TEF_GRID(d->n);
+    ProfScope pr(K_VALIDATION, ST);
+    val_append_kernel<<<a.nb_ev + TEF_GRID(a.HW), kThreads, 0, ST>>>(a);
     return (int)cudaGetLastError();
 }

@@ -25,6 +25,61 @@ def _cat(old, new, dim=1):
     return new if old is None else torch.cat([old, new], dim=dim)
 
 
+class _Rows:
+    """``[1, n, C]`` per-event rows with amortised O(1) append (capacity doubling) instead of a ``torch.cat`` of the whole
+    history per window; `view()` is the upstream tensor."""
+
+    def __init__(self, C, device):
+        self.C, self.device, self.buf, self.n = C, device, None, 0
+
+    def reserve(self, extra):
+        need = self.n + extra
+        cap = 0 if self.buf is None else self.buf.shape[1]
+        if need > cap:
+            nb = torch.empty((1, max(need, 2 * cap, 4096), self.C), dtype=torch.float32, device=self.device)
+            if self.n:
+                nb[:, :self.n].copy_(self.buf[:, :self.n])
+            self.buf = nb
+
+    def at(self, row):
+        return ctypes.c_void_p(self.buf.data_ptr() + 4 * self.C * row)
+
+    def view(self):
+        return None if self.buf is None else self.buf[:, :self.n]
+
+
+class _Stack:
+    """``[1, n, H, W]`` per-window maps, same idea."""
+
+    def __init__(self, res, device):
+        self.HW, self.res, self.device, self.buf, self.n = res[0] * res[1], res, device, None, 0
+
+    def reserve(self, extra=1):
+        need = self.n + extra
+        cap = 0 if self.buf is None else self.buf.shape[1]
+        if need > cap:
+            nb = torch.empty((1, max(need, 2 * cap, 16), self.res[0], self.res[1]), dtype=torch.float32, device=self.device)
+            if self.n:
+                nb[:, :self.n].copy_(self.buf[:, :self.n])
+            self.buf = nb
+
+    def at(self, slot):
+        return ctypes.c_void_p(self.buf.data_ptr() + 4 * self.HW * slot)
+
+    def view(self):
+        return None if self.buf is None else self.buf[:, :self.n]
+
+
+class _AppendDesc(ctypes.Structure):
+    """Mirror of ``tef_val_append``."""
+    _fields_ = [("events", ctypes.c_void_p), ("pol_mask", ctypes.c_void_p), ("n", ctypes.c_long), ("pass_index", ctypes.c_float),
+                ("ts_override", ctypes.c_void_p), ("ev_ts", ctypes.c_void_p), ("ev_loc", ctypes.c_void_p), ("ev_mask", ctypes.c_void_p),
+                ("fw_ts", ctypes.c_void_p), ("fw_loc", ctypes.c_void_p), ("fw_mask", ctypes.c_void_p), ("bw_loc", ctypes.c_void_p),
+                ("bw_mask", ctypes.c_void_p), ("flow", ctypes.c_void_p), ("event_mask", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("map_x", ctypes.c_void_p), ("map_y", ctypes.c_void_p), ("map_e", ctypes.c_void_p), ("prop_x", ctypes.c_void_p),
+                ("prop_y", ctypes.c_void_p)]
+
+
 def _tile4(t):
     return torch.cat([t, t, t, t], dim=1)
 
@@ -48,8 +103,17 @@ class BaseValidation(torch.nn.Module):
     # ------------------------------------------------------------------ state
     def _clear_base(self):
         self._passes = 0
-        self._event_ts = self._event_loc = self._event_pol_mask = None
-        self._flow_maps_x = self._flow_maps_y = self._event_mask = None
+        dev = self.device
+        self._r_ts, self._r_loc, self._r_mask = _Rows(1, dev), _Rows(2, dev), _Rows(2, dev)
+        self._s_x, self._s_y, self._s_e = _Stack(self.res, dev), _Stack(self.res, dev), _Stack(self.res, dev)
+
+    # upstream's attribute names, as views of the growing stores
+    _event_ts = property(lambda self: self._r_ts.view())
+    _event_loc = property(lambda self: self._r_loc.view())
+    _event_pol_mask = property(lambda self: self._r_mask.view())
+    _flow_maps_x = property(lambda self: self._s_x.view())
+    _flow_maps_y = property(lambda self: self._s_y.view())
+    _event_mask = property(lambda self: self._s_e.view())
 
     def reset_base(self):
         self._clear_base()
@@ -64,20 +128,57 @@ class BaseValidation(torch.nn.Module):
             ts[...] = ts.min() + 0.5                                             # loss/flow_val.py:87-88
         return ts
 
-    def update_base(self, flow_list, event_list, pol_mask, event_mask):
+    def update_base(self, flow_list, event_list, pol_mask, event_mask, iterative=None):
         """Append this window's events, finest flow map and event mask (upstream :75-114); the pass index is added to the
-        caller's timestamps in place, as upstream does."""
-        require_cuda(flow_list[-1], event_list, pol_mask)
+        caller's timestamps in place, as upstream does.  One launch (``tef_val_append_window``) fills every list `update`
+        appends to -- for the Iterative flavour (`iterative` = its row stores) also the forward / backward lists and the
+        propagated-flow stack."""
+        require_cuda(flow_list[-1], event_list, pol_mask, event_mask)
         if event_list.shape[0] != 1 or flow_list[-1].shape[0] != 1:
             raise RuntimeError("validation runs with batch size 1 (upstream builds batch-1 index grids, loss/flow_val.py:30-38)")
-        event_list[:, :, 0:1] += self._passes
-        self._event_ts = _cat(self._event_ts, self._window_ts(event_list))
-        self._event_loc = _cat(self._event_loc, event_list[:, :, 1:3].clone())
-        self._event_pol_mask = _cat(self._event_pol_mask, pol_mask.clone())
-        flow = flow_list[-1]
-        self._flow_maps_x = _cat(self._flow_maps_x, flow[:, 0:1])
-        self._flow_maps_y = _cat(self._flow_maps_y, flow[:, 1:2])
-        self._event_mask = _cat(self._event_mask, event_mask)
+        H, W = self.res
+        n, off, now = event_list.shape[1], self._r_ts.n, self._passes
+        if event_list.dim() != 3 or event_list.shape[2] != 4 or tuple(pol_mask.shape) != (1, n, 2):
+            raise ValueError("event_list must be [1,N,4] and pol_mask [1,N,2], got %s and %s" % (tuple(event_list.shape), tuple(pol_mask.shape)))
+        if tuple(flow_list[-1].shape) != (1, 2, H, W) or event_mask.numel() != H * W:
+            raise ValueError("flow must be [1,2,%d,%d] and the event mask [1,1,%d,%d]" % (H, W, H, W))
+        keep = []
+        d = _AppendDesc()
+        if event_list.is_contiguous() and event_list.dtype == torch.float32:
+            d.events, d.pass_index = event_list.data_ptr(), float(now)
+        else:
+            event_list[:, :, 0:1] += now
+            ev = event_list.contiguous().float()
+            keep.append(ev)
+            d.events, d.pass_index = ev.data_ptr(), 0.0
+        if self.config["loss"]["round_ts"] and n > 0:
+            # ts.min() + 0.5 of the timestamps AFTER the in-place update (loss/flow_val.py:86-88): two fp32 roundings, like upstream
+            ov = ((event_list[:, :, 0].min().float() + d.pass_index) + 0.5).reshape(1)
+            keep.append(ov)
+            d.ts_override = ov.data_ptr()
+        mk = pol_mask if (pol_mask.is_contiguous() and pol_mask.dtype == torch.float32) else pol_mask.contiguous().float()
+        fl = flow_list[-1] if (flow_list[-1].is_contiguous() and flow_list[-1].dtype == torch.float32) else flow_list[-1].contiguous().float()
+        em = event_mask if (event_mask.is_contiguous() and event_mask.dtype == torch.float32) else event_mask.contiguous().float()
+        keep += [mk, fl, em]
+        rows = [self._r_ts, self._r_loc, self._r_mask] + (list(iterative["rows"]) if iterative else [])
+        stacks = [self._s_x, self._s_y, self._s_e] + (list(iterative["stacks"]) if iterative else [])
+        for r in rows:
+            r.reserve(n)
+        for st in stacks:
+            st.reserve(1)
+        d.pol_mask, d.n, d.flow, d.event_mask, d.H, d.W = mk.data_ptr(), n, fl.data_ptr(), em.data_ptr(), H, W
+        d.ev_ts, d.ev_loc, d.ev_mask = self._r_ts.at(off), self._r_loc.at(off), self._r_mask.at(off)
+        d.map_x, d.map_y, d.map_e = self._s_x.at(now), self._s_y.at(now), self._s_e.at(now)
+        if iterative:
+            fw_ts, fw_loc, fw_mask, bw_loc, bw_mask = iterative["rows"]
+            d.fw_ts, d.fw_loc, d.fw_mask, d.bw_loc, d.bw_mask = fw_ts.at(off), fw_loc.at(off), fw_mask.at(off), bw_loc.at(off), bw_mask.at(off)
+            d.prop_x, d.prop_y = iterative["stacks"][0].at(now), iterative["stacks"][1].at(now)
+        check(lib().tef_val_append_window(ctypes.byref(d), stream()), "tef_val_append_window")
+        for r in rows:
+            r.n += n
+        for st in stacks:
+            st.n += 1
+        return off, n
 
     # ------------------------------------------------------- building blocks
     def _pol_images(self, loc, pol_mask, round_idx, extra=None):
@@ -169,8 +270,8 @@ class Linear(BaseValidation):
         self._event_flow = None
 
     def update(self, flow_list, event_list, pol_mask, event_mask):
-        self.update_base(flow_list, event_list, pol_mask, event_mask)
-        flow = get_event_flow(self._flow_maps_x[:, -1], self._flow_maps_y[:, -1], event_list[:, :, 1:3])
+        off, n = self.update_base(flow_list, event_list, pol_mask, event_mask)
+        flow = get_event_flow(self._flow_maps_x[:, -1], self._flow_maps_y[:, -1], self._event_loc[:, off:off + n])
         self._event_flow = _cat(self._event_flow, flow)
         self._passes += 1
 
@@ -212,60 +313,59 @@ class Iterative(BaseValidation):
         self._clear_iterative()
 
     def _clear_iterative(self):
-        self._fw_event_loc = self._fw_event_warp_ts = self._fw_event_pol_mask = None
-        self._bw_event_loc = self._bw_event_pol_mask = None
-        self._fw_prop_flow_maps_x = self._fw_prop_flow_maps_y = None
+        dev = self.device
+        self._r_fw_ts, self._r_fw_loc, self._r_fw_mask = _Rows(1, dev), _Rows(2, dev), _Rows(2, dev)
+        self._r_bw_loc, self._r_bw_mask = _Rows(2, dev), _Rows(2, dev)
+        self._s_px, self._s_py = _Stack(self.res, dev), _Stack(self.res, dev)
         self._accum_flow_map_x = self._accum_flow_map_y = None
         self._flow_warping_indices = None
+        self._prop_acc = None
         self._flow_out_mask = torch.zeros(1, 1, self.res[0], self.res[1], device=self.device)
+
+    _fw_event_warp_ts = property(lambda self: self._r_fw_ts.view())
+    _fw_event_loc = property(lambda self: self._r_fw_loc.view())
+    _fw_event_pol_mask = property(lambda self: self._r_fw_mask.view())
+    _bw_event_loc = property(lambda self: self._r_bw_loc.view())
+    _bw_event_pol_mask = property(lambda self: self._r_bw_mask.view())
+    _fw_prop_flow_maps_x = property(lambda self: self._s_px.view())
+    _fw_prop_flow_maps_y = property(lambda self: self._s_py.view())
 
     def reset(self):
         self.reset_base()
         self._clear_iterative()
 
-    def update_fw_event_lists(self, event_list, event_pol_mask):
-        self._fw_event_warp_ts = _cat(self._fw_event_warp_ts, self._window_ts(event_list)).contiguous()
-        self._fw_event_loc = _cat(self._fw_event_loc, event_list[:, :, 1:3].clone()).contiguous()
-        self._fw_event_pol_mask = _cat(self._fw_event_pol_mask, event_pol_mask.float().clone()).contiguous()
-
-    def update_bw_event_lists(self, event_loc, event_pol_mask):
-        self._bw_event_loc = _cat(self._bw_event_loc, event_loc.clone())
-        self._bw_event_pol_mask = _cat(self._bw_event_pol_mask, event_pol_mask.clone())
-
     def update(self, flow_list, event_list, pol_mask, event_mask):
-        self.update_base(flow_list, event_list, pol_mask, event_mask)
+        """Upstream ``Iterative.update`` (:477-607) in seven launches: append (all lists and stacks), forward step of every
+        event so far, backward chain of the new window, flow propagation (clear, splat, normalise), pixel trajectories."""
         now = self._passes
         H, W = self.res
         L, st = lib(), stream()
-        maps_x, maps_y = self._flow_maps_x.contiguous(), self._flow_maps_y.contiguous()          # [1,now+1,H,W]
-        last = now * H * W * 4
-        last_x, last_y = ctypes.c_void_p(maps_x.data_ptr() + last), ctypes.c_void_p(maps_y.data_ptr() + last)
+        off, n = self.update_base(flow_list, event_list, pol_mask, event_mask,
+                                  iterative={"rows": (self._r_fw_ts, self._r_fw_loc, self._r_fw_mask, self._r_bw_loc, self._r_bw_mask),
+                                             "stacks": (self._s_px, self._s_py)})
+        last_x, last_y = self._s_x.at(now), self._s_y.at(now)
 
         # all events so far, one window forward with the newest map (upstream :483-517)
-        self.update_fw_event_lists(event_list, pol_mask)
-        check(L.tef_val_forward_step(last_x, last_y, ptr(self._fw_event_loc), ptr(self._fw_event_warp_ts), ptr(self._fw_event_pol_mask),
-                                     _f(now + 1), _l(self._fw_event_loc.shape[1]), H, W, st), "tef_val_forward_step")
+        check(L.tef_val_forward_step(last_x, last_y, self._r_fw_loc.at(0), self._r_fw_ts.at(0), self._r_fw_mask.at(0), _f(now + 1), _l(off + n), H, W, st),
+              "tef_val_forward_step")
 
-        # the new window, back to time 0 through every map (upstream :519-556)
-        loc = event_list[:, :, 1:3].clone(memory_format=torch.contiguous_format)
-        mask = pol_mask.float().clone(memory_format=torch.contiguous_format)
-        ts = self._window_ts(event_list).contiguous()
-        check(L.tef_val_backward_chain(ptr(maps_x), ptr(maps_y), now + 1, ptr(loc), ptr(ts), ptr(mask), _l(loc.shape[1]), H, W, st),
-              "tef_val_backward_chain")
-        self.update_bw_event_lists(loc, mask)
+        # the new window, back to time 0 through every map (upstream :519-556): its rows of the backward lists, in place
+        check(L.tef_val_backward_chain(self._s_x.at(0), self._s_y.at(0), now + 1, self._r_bw_loc.at(off), self._r_ts.at(off), self._r_bw_mask.at(off),
+                                       _l(n), H, W, st), "tef_val_backward_chain")
 
-        # older flow maps carried one window forward (upstream :558-577)
-        newest = flow_list[-1]
-        self._fw_prop_flow_maps_x = _cat(self._fw_prop_flow_maps_x, newest[:, 0:1])
-        self._fw_prop_flow_maps_y = _cat(self._fw_prop_flow_maps_y, newest[:, 1:2])
+        # older flow maps carried one window forward (upstream :558-577), in place in the propagated stack
         if now > 0:
-            self._prop_flow(self._fw_prop_flow_maps_x, self._fw_prop_flow_maps_y, 0, now, None, self._fw_prop_flow_maps_x, self._fw_prop_flow_maps_y)
+            if self._prop_acc is None or self._prop_acc.shape[0] < now:
+                self._prop_acc = torch.empty((max(now, 2 * (0 if self._prop_acc is None else self._prop_acc.shape[0]), 16), 3, H, W), dtype=torch.float32,
+                                             device=self.device)
+            check(L.tef_val_forward_prop_flow(self._s_px.at(0), self._s_py.at(0), 0, now, 1, _f(0.0), ptr(self._prop_acc), self._s_px.at(0), self._s_py.at(0),
+                                              H, W, st), "tef_val_forward_prop_flow")
 
         # pixel trajectories (upstream :579-605)
         if self._flow_warping_indices is None:
             self._flow_warping_indices = self.indices_map.clone()
-        self._accum_flow_map_x = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
-        self._accum_flow_map_y = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
+            self._accum_flow_map_x = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
+            self._accum_flow_map_y = torch.empty((1, 1, H, W), dtype=torch.float32, device=self.device)
         check(L.tef_val_trajectory_step(last_x, last_y, ptr(self._flow_warping_indices), ptr(self._flow_out_mask), ptr(self._accum_flow_map_x),
                                         ptr(self._accum_flow_map_y), H, W, st), "tef_val_trajectory_step")
         self._passes += 1
