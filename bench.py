@@ -383,7 +383,7 @@ def measure_l2_rates(L, dev):
     buf = torch.zeros(64 << 20, dtype=torch.uint8, device=dev)     # L2-resident (126 MB L2)
     out = {}
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for name, kind, mode in (("red_v4_spread", 0, 0), ("red_v4_local", 0, 1), ("gather8_spread", 1, 0), ("gather8_local", 1, 1),
+    for name, kind, mode in (("red_v4_spread", 0, 0), ("red_v4_local", 0, 1), ("red_v4_tile_sorted", 0, 10), ("gather8_spread", 1, 0), ("gather8_local", 1, 1),
                              ("gather16_spread", 2, 0), ("gather16_local", 2, 1)):
         ops = ctypes.c_long()
         best = 1e30
@@ -722,6 +722,19 @@ def run_ours(args, wl):
                 l2["kernels"][k] = {"gathers16": int(ops["gathers"]), "red_v4": int(ops["reds"]), "ms_gathers_at_peak": round(t_g * 1e3, 4),
                                     "ms_reds_at_peak": round(t_r * 1e3, 4), "bound": "gather" if t_g >= t_r else "red",
                                     "frac": round(t_min * 1e3 / kern[k]["ms_avg"], 4)}
+        # The unit both event kernels run closest to: the SM's L1TEX path moves about one scattered
+        # 16-byte lane access per cycle -- every lane of a red.v4, every distinct sector of a gather or store.  Sector counts per
+        # launch come from the committed ncu capture of this workload (profiles/traffic.json), the time is measured live, the
+        # peak is the red.v4 lane rate of the tile-sorted micro-benchmark on this GPU.
+        l1 = None
+        tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        sect = tj.get(wl["name"], {}).get("l1tex_lane_sectors")
+        if sect:
+            l1 = {"peak_G_per_s": round(rates["red_v4_tile_sorted"], 1), "unit": "G lane-sectors/s", "source": tj.get("_l1tex_source"), "kernels": {}}
+            for k, n in sect.items():
+                if k in kern:
+                    a = n / (kern[k]["ms_avg"] * 1e-3) / 1e9
+                    l1["kernels"][k] = {"lane_sectors_per_launch": int(n), "achieved": round(a, 1), "frac": round(a / rates["red_v4_tile_sorted"], 4)}
         try:
             enc_roof = encoding_roofline(L, dev, hbm)
         except Exception as exc:
@@ -760,7 +773,7 @@ def run_ours(args, wl):
                                     "steps": e2e_steps, "ms_per_step": ms_full / e2e_steps, "loss": loss_full,
                                     "h2d_gbps_per_gpu_while_copying": round(h2d_full / (cp_full * 1e-3) / 1e9, 2),
                                     "note": "round 1's e2e: the reference's own fp32 tensors (24 B per event) and the flow maps up, all gradients down"},
-            "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "roofline_encodings": enc_roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_l2_ops": l2, "roofline_l1tex": l1, "roofline_encodings": enc_roof, "cpu_baseline": cpu,
             "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"], "share_of_step": round(v["ms_total"] / prof_steps / ms_prof, 4)}
                         for k, v in kern.items()},
             "kernels_note": "per-kernel CUDA events in a second pass of %d steps at %.4f ms/step (the events themselves cost the difference to ms_per_step)" % (prof_steps, ms_prof),
@@ -827,7 +840,8 @@ def run_train(args, wl, quiet=False):
     if mode == "graph":
         # static inputs of the captured step; a step's events are copied in before the replay (inside the timed region)
         static = [(src[t][0].clone(), masks[t][0], src[t][1].clone(), masks[t][1]) for t in range(P)]
-        graphed = GraphedTrainStep(model, loss_fn, opt, static, flow_scaling=32.0, clip_grad=100.0, encode=encode, reducer=reducer, autocast=autocast)
+        graphed = GraphedTrainStep(model, loss_fn, opt, static, flow_scaling=32.0, clip_grad=100.0, encode=encode, reducer=reducer, autocast=autocast,
+                                   capture_collectives=os.environ.get("TEF_TRAIN_CAPTURE_NCCL", "0") == "1")
 
         def step(i):
             for t in range(P):
@@ -866,7 +880,8 @@ def run_train(args, wl, quiet=False):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
            "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch/cuDNN, channels_last, %s, 31.4M params)" % (("bf16 autocast, %s flow heads, fp32 CM loss" % ("fp32" if fp32_heads else "bf16")) if autocast else "fp32/TF32"),
-                          step_mode=("one CUDA graph over forward + CM loss + backward; all-reduce, clip, Adam eager" if mode == "graph" else "eager"),
+                          step_mode=(("one CUDA graph over forward + CM loss + backward%s; clip, Adam eager" % (" + the bucketed all-reduces" if graphed.comm_captured else "; all-reduce after the replay"))
+                                     if mode == "graph" else "eager"),
                           optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets) under the backward pass" % len(reducer.buckets)),
            "loss": float(loss.item()), "events_per_step": B_global * P * (wl["N"] + wl["Nd"])}
     if own_pg:

@@ -128,9 +128,9 @@ typedef struct tef_update_desc {
     long rows[2];                          /* B * n                                               */
     float pass_index[2];
     const float *ts_override[2];           /* round_ts device scalars or NULL                     */
-    void *sort_bins;                       /* optional fused tile-sort histogram: int [2*P*B*tiles*128 + 1] of the window, where
+    void *sort_bins;                       /* optional fused tile-sort histogram: int [2*P*B*tiles*256 + 1] of the window, where
                                               tiles = ceil(W/16)*ceil(H/8); segment (set k, pass t) owns bins from
-                                              (k*P + t)*B*tiles*128 (the layout tef_*_forward expects with hist_done = 1) */
+                                              (k*P + t)*B*tiles*256 (the layout tef_*_forward expects with hist_done = 1) */
     int hist;                              /* 1: count this pass' events into sort_bins            */
     int zero_bins;                         /* 1: clear sort_bins first (first update of a window)  */
     /* strided[k] = 1: events[k] / masks[k] are NOT contiguous rows; element (b, row, col) of the [B][n][4] event tensor is at
@@ -258,6 +258,9 @@ typedef struct tef_val_append {
     float *map_x; float *map_y; float *map_e; float *prop_x; float *prop_y;
 } tef_val_append;
 int tef_val_append_window(const tef_val_append *d, void *stream);
+/* _pol_images of the criteria (:116-131 and the images of FWL / RSAT, :189-274): get_interpolation + optional per-event weight
+   `extra` [n] (NULL: none) + one interpolate per polarity, fused: loc [n][2] (y, x), mask [n][2] -> out [2][H][W] (zeroed inside) */
+int tef_val_pol_images(const float *loc, const float *mask, const float *extra, float *out, long n, int H, int W, int round_idx, void *stream);
 /* Iterative.update :483-517: every accumulated event one window forward with the newest map, in place:
    loc [n][2] (y, x), ts [n] (set to tref), mask [n][2] */
 int tef_val_forward_step(const float *mapx, const float *mapy, float *loc, float *ts, float *mask, float tref, long n, int H, int W,

@@ -2,7 +2,7 @@
 # round 2, GPU call D (N GPUs): validation rewrite tests + bench, then the multi-GPU arms at N = $1
 N=${1:-2}
 mkdir -p gpurun_out
-if [ "$N" = "2" ]; then
+if [ "$2" = "single" ]; then
   timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.log
   grep -E "passed|failed|FAILED|rc=|Error" gpurun_out/r2d_pytest.log | tail -15
   for wl in validation_480x640_100kev validation_480x640_500kev; do timeout 200 python bench.py --workload $wl --steps 10 >> gpurun_out/r2d_validation.json 2>> gpurun_out/r2d.err; done

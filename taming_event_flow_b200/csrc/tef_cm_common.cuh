@@ -26,18 +26,25 @@ struct SegTable {
 struct SortGeom {
     int blk_off[kMaxSeg + 1];        // CTA ranges of the sort kernels (4 rows per thread)
     int B, H, W, tiles_x, tiles;     // 16x8-pixel tiles per sample
-    long nbins;                      // nseg * B * tiles * 128
+    long nbins;                      // nseg * B * tiles * kBinsPerTile
     int *bins;                       // [nbins + 1] histogram -> offsets -> bin ends
     int *sums;                       // scan scratch, one int per 2048 bins
     float4 *rec;                     // sorted rows, 32 B each: (ts, y, x, sample index bits | mask+, mask-, 0, 0)
 };
 
-// Sort key of one event inside its segment: (sample, 16x8-pixel tile, pixel).  `first_bin` is the segment's first bin.
-__device__ __forceinline__ int sort_bin(int first_bin, int tiles_x, int tiles, int H, int W, int b, float y, float x) {
+// Sort key of one event inside its segment: (sample, 16x8-pixel tile, pixel, polarity).  `first_bin` is the segment's first bin.
+// Polarity is part of the key because the images are polarity-planar: two events of one pixel reduce into the same slots (and
+// gather the same gradient-image sectors) only if they have the same polarity, so grouping them doubles what the
+// neighbour-lane merge of the event kernels finds (DESIGN.md decision 20).
+constexpr int kBinsPerTile = 256;    // 16 x 8 pixels x 2 polarities
+__device__ __forceinline__ int sort_bin(int first_bin, int tiles_x, int tiles, int H, int W, int b, float y, float x, int neg) {
     const int iy = (int)fminf(fmaxf(floorf(y), 0.0f), (float)(H - 1));
     const int ix = (int)fminf(fmaxf(floorf(x), 0.0f), (float)(W - 1));
     const int tile = (iy >> 3) * tiles_x + (ix >> 4);
-    return first_bin + (b * tiles + tile) * 128 + ((iy & 7) << 4) + (ix & 15);
+#ifdef TEF_SORT_NO_POL
+    neg = 0;                          // A/B build: round 1's key (sample, tile, pixel)
+#endif
+    return first_bin + (b * tiles + tile) * kBinsPerTile + ((((iy & 7) << 4) + (ix & 15)) << 1) + neg;
 }
 
 // One entry per temporal scale (loss/flow.py:42-44, :434-441, :657-668)
@@ -204,9 +211,9 @@ inline int fill_params(const tef_cm_desc *d, int linear, CmParams &p) {
     g.tiles_x = (d->W + 15) / 16; g.tiles = g.tiles_x * ((d->H + 7) / 8);
     // bins are laid out by FIXED segment slots (set * P + pass), empty passes included, so that tef_update_pass can count
     // a pass before the later ones are known; the detached set's slots exist only if it has any rows
-    if (2l * d->P * d->B * g.tiles * 128 > 0x7fffffffl) return TEF_ELIMIT;          // bin indices are 32-bit
+    if (2l * d->P * d->B * g.tiles * kBinsPerTile > 0x7fffffffl) return TEF_ELIMIT;  // bin indices are 32-bit
     if ((long)d->B * 4 * p.ig.plane > 0x7fffffffl) return TEF_ELIMIT;               // merge keys (sample * slot size + offset) are 31-bit
-    const int per_seg = d->B * g.tiles * 128;
+    const int per_seg = d->B * g.tiles * kBinsPerTile;
     bool any_detached = false;
     for (int s = 0; s < ns; ++s) {
         p.seg.first_bin[s] = (p.seg.set[s] * d->P + p.seg.pass[s]) * per_seg;

@@ -54,7 +54,7 @@ __device__ __forceinline__ void stage_two_body(const StageTwo &s, int blk) {
     s.ev_out[k][i] = e;
     s.mk_out[k][i] = m;
     if (s.bins && !(m.x == 0.0f && m.y == 0.0f))
-        atomicAdd(s.bins + sort_bin(s.first_bin[k], s.tiles_x, s.tiles, s.H, s.W, (int)(i / s.n[k]), e.y, e.z), 1);
+        atomicAdd(s.bins + sort_bin(s.first_bin[k], s.tiles_x, s.tiles, s.H, s.W, (int)(i / s.n[k]), e.y, e.z, m.x == 0.0f), 1);
 }
 struct FlowPtrs { const float *p[TEF_MAX_FLOWS]; };
 
@@ -197,7 +197,7 @@ extern "C" int tef_update_pass(const tef_update_desc *u, void *stream) {
     if (u->hist) {
         if (!u->sort_bins || u->t < 0 || u->t >= u->P || u->B < 1) return TEF_EINVAL;
         s.tiles_x = (u->W + 15) / 16; s.tiles = s.tiles_x * ((u->H + 7) / 8); s.H = u->H; s.W = u->W;
-        const long per_seg = (long)u->B * s.tiles * 128;
+        const long per_seg = (long)u->B * s.tiles * kBinsPerTile;
         if (2 * u->P * per_seg > 0x7fffffffl) return TEF_ELIMIT;
         if (u->zero_bins) cudaMemsetAsync(u->sort_bins, 0, sizeof(int) * (2 * u->P * per_seg + 1), st);
         s.bins = (int *)u->sort_bins;

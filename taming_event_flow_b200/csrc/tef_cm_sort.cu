@@ -3,7 +3,7 @@
 // Why: with events in arrival (time) order every bilinear gather and every image reduction of a warp
 // touches ~32 different L2 sectors, and both loss kernels saturate the L1/L2 transaction rate
 // (profiles/r1_a_*: 30.7 sectors per load request, 15.4 per RED request, L1 hit 21 %).  The loss is a sum
-// over events, so their order is free: sorting each (set, pass) segment by (sample, 16x8-pixel tile, pixel)
+// over events, so their order is free: sorting each (set, pass) segment by (sample, 16x8-pixel tile, pixel, polarity)
 // makes the lanes of a warp start from the same few pixels and, the flow being smooth, stay neighbours
 // along the whole warping chain.  Padding rows (mask 0,0) are dropped on the way.
 //
@@ -15,8 +15,8 @@
 
 namespace tef {
 
-__device__ __forceinline__ int bin_of(const CmParams &p, int seg, int b, float y, float x) {
-    return sort_bin(p.seg.first_bin[seg], p.sort.tiles_x, p.sort.tiles, p.sort.H, p.sort.W, b, y, x);
+__device__ __forceinline__ int bin_of(const CmParams &p, int seg, int b, float y, float x, float2 m) {
+    return sort_bin(p.seg.first_bin[seg], p.sort.tiles_x, p.sort.tiles, p.sort.H, p.sort.W, b, y, x, m.x == 0.0f);
 }
 
 // Both kernels walk a segment with kSortIlp rows per thread (strided by the CTA size, so every access stays
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kThreads) sort_hist_kernel(const __grid_consta
 #pragma unroll
     for (int k = 0; k < kSortIlp; ++k) {
         if (m[k].x == 0.0f && m[k].y == 0.0f) continue;            // padding rows are dropped
-        atomicAdd(p.sort.bins + bin_of(p, sg, (int)(row[k] / n), e[k].y, e[k].z), 1);
+        atomicAdd(p.sort.bins + bin_of(p, sg, (int)(row[k] / n), e[k].y, e[k].z, m[k]), 1);
     }
 }
 
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const __grid_con
         dst[k] = -1;
         if (m[k].x == 0.0f && m[k].y == 0.0f) continue;
         const int b = (int)(row[k] / n);
-        dst[k] = atomicAdd(p.sort.bins + bin_of(p, sg, b, e[k].y, e[k].z), 1);
+        dst[k] = atomicAdd(p.sort.bins + bin_of(p, sg, b, e[k].y, e[k].z, m[k]), 1);
         e[k].w = __int_as_float(b);
     }
     // one 256-bit store per event (STG.E.ENL2.256): a full, aligned 32-byte sector, so the scattered writes never

@@ -107,6 +107,43 @@ __global__ void __launch_bounds__(kThreads) val_trajectory_kernel(const float *_
     accy[p] = ny - (float)(p / r.W);
 }
 
+// _pol_images of the validation criteria (loss/flow_val.py:116-131, :189-274): get_interpolation, the optional per-event
+// weight (`weights * extra`), and one interpolate per polarity -- the operator route's arithmetic, event by event:
+// value = ((corner weight) * extra) * mask_c reduced into out[c][pixel]; out [2][H][W] is zeroed by the caller.
+__global__ void __launch_bounds__(kThreads) val_pol_images_kernel(const float2 *__restrict__ loc, const float2 *__restrict__ mask,
+                                                                  const float *__restrict__ extra, float *__restrict__ out, long n, Res r, int round_idx) {
+    const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const long HW = (long)r.H * r.W;
+    const float2 l = loc[i], m = mask[i];
+    const bool has_ex = extra != nullptr;
+    const float ex = has_ex ? extra[i] : 1.0f;
+    if (round_idx) {
+        const float ry = rintf(l.x), rx = rintf(l.y);              // torch.round: half to even (utils/iwe.py:79)
+        const float ok = (ry >= 0.f && ry < (float)r.H && rx >= 0.f && rx < (float)r.W) ? 1.0f : 0.0f;
+        const long px = (long)((ry * ok) * (float)r.W + rx * ok);
+        float w = (1.0f * 1.0f) * ok;
+        if (has_ex) w = w * ex;
+        const float vp = w * m.x, vn = w * m.y;
+        if (vp != 0.0f) red_add_f32(out + px, vp);
+        if (vn != 0.0f) red_add_f32(out + HW + px, vn);
+        return;
+    }
+    Corners c;
+    corners(l.x, l.y, r, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ky = k >> 1, kx = k & 1;
+        const float ok = (c.oky[ky] && c.okx[kx]) ? 1.0f : 0.0f;
+        const long px = (long)((c.cy[ky] * ok) * (float)r.W + c.cx[kx] * ok);               // utils/iwe.py:104,:110-111
+        float w = (c.wy[ky] * c.wx[kx]) * ok;                                               // :107
+        if (has_ex) w = w * ex;
+        const float vp = w * m.x, vn = w * m.y;
+        if (vp != 0.0f) red_add_f32(out + px, vp);
+        if (vn != 0.0f) red_add_f32(out + HW + px, vn);
+    }
+}
+
 // One launch for everything `update` appends (loss/flow_val.py:75-114, :483-487, :519-528, :558-562): CTAs [0, nb_ev) copy the
 // window's events into the row arrays (raw list, forward list, backward list), adding the pass index to the caller's
 // timestamps in place; the other CTAs copy the newest flow map and event mask into the per-window map stacks.
@@ -201,5 +238,15 @@ extern "C" int tef_val_append_window(const tef_val_append *d, void *stream) {
     a.nb_ev = (int)TEF_GRID(d->n);
     ProfScope pr(K_VALIDATION, ST);
     val_append_kernel<<<a.nb_ev + TEF_GRID(a.HW), kThreads, 0, ST>>>(a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tef_val_pol_images(const float *loc, const float *mask, const float *extra, float *out, long n, int H, int W, int round_idx, void *stream) {
+    if (n < 0 || H < 2 || W < 2 || !out) return TEF_EINVAL;
+    cudaMemsetAsync(out, 0, sizeof(float) * 2 * (long)H * W, ST);
+    if (n == 0) return 0;
+    if (!loc || !mask) return TEF_EINVAL;
+    ProfScope pr(K_VALIDATION, ST);
+    val_pol_images_kernel<<<TEF_GRID(n), kThreads, 0, ST>>>((const float2 *)loc, (const float2 *)mask, extra, out, n, Res::make(H, W), round_idx);
     return (int)cudaGetLastError();
 }

@@ -293,7 +293,7 @@ class BaseEventWarping(torch.nn.Module):
         elif _FUSED_HIST and (t == 0 or w.hist_valid):
             # the staging kernel also counts the events into the tile-sort histogram (saves the forward a pass over them)
             tiles = ((W + 15) // 16) * ((H + 7) // 8)
-            bins = w.ws.get("bins", (2 * P * B * tiles * 128 + 1,), torch.int32, dev)
+            bins = w.ws.get("bins", (2 * P * B * tiles * 256 + 1,), torch.int32, dev)      # 16 x 8 pixels x 2 polarities per tile
             u.sort_bins, u.hist, u.zero_bins = bins.data_ptr(), 1, int(t == 0)
             w.hist_valid = True
         check(self._fn_update(ctypes.byref(u), stream()), "tef_update_pass")

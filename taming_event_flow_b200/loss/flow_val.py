@@ -182,7 +182,16 @@ class BaseValidation(torch.nn.Module):
 
     # ------------------------------------------------------- building blocks
     def _pol_images(self, loc, pol_mask, round_idx, extra=None):
-        """Per-polarity images of (optionally weighted) events at `loc`: [B,2,H,W]."""
+        """Per-polarity images of (optionally weighted) events at `loc`: [B,2,H,W].  Batch 1 with contiguous fp32 inputs (what
+        the criteria hold) is one fused launch; anything else goes through the stand-alone operators, same arithmetic."""
+        if (loc.shape[0] == 1 and loc.is_contiguous() and pol_mask.is_contiguous() and loc.dtype == torch.float32 and pol_mask.dtype == torch.float32
+                and pol_mask.shape[-1] == 2 and (extra is None or (extra.is_contiguous() and extra.dtype == torch.float32 and extra.numel() == loc.shape[1]))):
+            require_cuda(loc, pol_mask, extra)
+            H, W = self.res
+            out = torch.empty((1, 2, H, W), dtype=torch.float32, device=loc.device)
+            check(lib().tef_val_pol_images(ptr(loc), ptr(pol_mask), ptr(extra), ptr(out), _l(loc.shape[1]), H, W, int(bool(round_idx)), stream()),
+                  "tef_val_pol_images")
+            return out
         idx, w = get_interpolation(loc, self.res, round_idx=round_idx)
         pm = pol_mask if round_idx else _tile4(pol_mask)
         if extra is not None:

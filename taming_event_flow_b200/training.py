@@ -194,7 +194,7 @@ class GraphedTrainStep:
     states from one loss window to the next and detaches them, ``train_flow.py:136``)."""
 
     def __init__(self, model, loss_fn, optimizer, windows, flow_scaling=32.0, clip_grad=100.0, encode=None, reducer=None, autocast=None,
-                 warmup=2):
+                 warmup=2, capture_collectives=False):
         self.model, self.loss_fn, self.opt, self.windows = model, loss_fn, optimizer, windows
         self.flow_scaling, self.clip_grad, self.encode, self.autocast = flow_scaling, clip_grad, encode, autocast
         self.reducer = reducer if reducer is not None else GradReducer(list(model.parameters()), world_size=1)
@@ -211,12 +211,18 @@ class GraphedTrainStep:
         # the recurrent states become static tensors: read at the start of every replay, written back at its end
         self.states = [s.detach().clone() for s in model.states]
         self.graph = torch.cuda.CUDAGraph()
-        overlap, self.reducer.overlap = self.reducer.overlap, False          # collectives are issued after the replay, not captured
+        # capture_collectives: the bucketed all-reduces the gradient hooks issue (on NCCL's stream, forked from the capturing
+        # stream) become branches of the graph and overlap the tail of the captured backward pass; otherwise they are issued
+        # after the replay
+        self.comm_captured = bool(capture_collectives and self.reducer.world_size > 1)
+        overlap, self.reducer.overlap = self.reducer.overlap, self.comm_captured
         try:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, **({"capture_error_mode": "thread_local"} if self.comm_captured else {})):
                 self.reducer.zero()
                 model.states = list(self.states)
                 self.loss = self._fwd_bwd()
+                if self.comm_captured:
+                    self.reducer.finish()
                 for dst, src in zip(self.states, model.states):
                     dst.copy_(src.detach())
         finally:
@@ -234,13 +240,14 @@ class GraphedTrainStep:
         self.model.detach_states()
         return loss.detach()
 
-    def _tail(self):
-        self.reducer.finish()
+    def _tail(self, reduce=True):
+        if reduce:
+            self.reducer.finish()
         if self.clip_grad is not None:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_grad)
         self.opt.step()
 
     def step(self):
         self.graph.replay()
-        self._tail()
+        self._tail(reduce=not self.comm_captured)
         return self.loss
