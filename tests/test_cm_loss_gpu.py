@@ -620,3 +620,62 @@ def test_quad_cell_copies_give_the_same_results(monkeypatch):
     oc = orc.make_cfg(B, H, W, P, F, 1, "two", True)
     o = orc.iterative(oc, seq["flows"], seq["events"], seq["masks"], seq["d_events"], seq["d_masks"], np.float32, want_grad=True, want_iwe=True)
     assert rel_err(out[True]["gflow"], o["gflow"])[0] < TOL and rel_err(out[True]["iwe"], o["iwe"])[0] < TOL
+
+
+def test_graphed_loss_window_replays_the_eager_result():
+    """taming_event_flow_b200.graphs.GraphedLossWindow: update x P -> forward -> backward captured once and replayed as one CUDA
+    graph.  Same loss and gradients as the eager API; new contents of the static inputs give the new window's result; the
+    static inputs keep their timestamps (the in-place `ts += pass` happens on private copies inside the graph)."""
+    from taming_event_flow_b200.graphs import GraphedLossWindow
+
+    B, P, N, Nd, H, W, F = 2, 4, 1200, 300, 40, 48, 2
+    cfg = syn.loss_config(H, W, B, P)
+    seqs = [syn.make_sequence(70 + k, B, P, N, Nd, H, W, F, 2.0) for k in range(2)]
+    eager = [_run_gpu("iterative", cfg, s["flows"], s["events"], s["masks"], s["d_events"], s["d_masks"]) for s in seqs]
+    s0 = seqs[0]
+    static = {k: [x.cuda().clone() for x in s0[k]] for k in ("events", "masks", "d_events", "d_masks")}
+    flows = [[f.cuda().clone() for f in per] for per in s0["flows"]]
+    gw = GraphedLossWindow(_module("iterative", cfg), flows, static["events"], static["masks"], static["d_events"], static["d_masks"])
+    assert gw.launches_per_replay == P + 4 + 3 + 3              # update x P, sort (3 scans + scatter), forward (3), backward (3)
+    for k, s in enumerate(seqs):
+        for t in range(P):
+            for key in ("events", "masks", "d_events", "d_masks"):
+                static[key][t].copy_(s[key][t])
+            for f in range(F):
+                gw.flows[t][f].data.copy_(s["flows"][t][f])
+        loss, grads = gw.replay()
+        g = np.stack([np.stack([grads[t][f].cpu().numpy() for t in range(P)]) for f in range(F)])
+        assert abs(loss.item() - eager[k]["loss"]) <= 1e-6 * abs(eager[k]["loss"])
+        assert rel_err(g, eager[k]["gflow"])[0] < 1e-6
+        assert torch.equal(static["events"][P - 1].cpu(), s["events"][P - 1])          # untouched by the replay
+
+
+def test_graphed_train_step_follows_the_eager_step():
+    """training.GraphedTrainStep (forward over P windows + CM loss + backward as one CUDA graph, flat gradients, eager clip + Adam)
+    against the eager train_step from the same initial weights: same loss trajectory."""
+    from taming_event_flow_b200.flownet import RecEVFlowNet
+    from taming_event_flow_b200.loss.flow import Iterative
+    from taming_event_flow_b200.training import GradReducer, GraphedTrainStep, train_step
+
+    B, P, N, H, W = 2, 4, 1500, 64, 64
+    seq = syn.make_sequence(21, B, P, N, 500, H, W, 1, 1.0)
+    wins = [(seq["events"][t].cuda(), seq["masks"][t].cuda(), seq["d_events"][t].cuda(), seq["d_masks"][t].cuda()) for t in range(P)]
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        model = RecEVFlowNet(num_bins=2, base_channels=8).cuda()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        red = GradReducer(list(model.parameters()), world_size=1)
+        loss_fn = Iterative(syn.loss_config(H, W, B, P), "cuda")
+        losses = []
+        if mode == "eager":
+            for _ in range(5):
+                losses.append(train_step(model, loss_fn, opt, [(e.clone(), m, d.clone(), dm) for e, m, d, dm in wins], reducer=red).item())
+        else:
+            static = [(e.clone(), m, d.clone(), dm) for e, m, d, dm in wins]
+            g = GraphedTrainStep(model, loss_fn, opt, static, reducer=red, warmup=2)       # two eager warm-up steps, then replays
+            losses = [None, None] + [g.step().item() for _ in range(3)]
+        out[mode] = losses
+    assert all(np.isfinite(out["eager"]))
+    for a, b in zip(out["eager"][2:], out["graph"][2:]):
+        assert abs(a - b) <= 2e-3 * abs(a), (out["eager"], out["graph"])
