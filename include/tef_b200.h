@@ -279,6 +279,38 @@ int tef_val_forward_prop_flow(const float *mapsx, const float *mapsy, int first,
 int tef_val_trajectory_step(const float *mapx, const float *mapy, float *idx, float *out_mask, float *accx, float *accy, int H, int W,
                             void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* The training step around the loss: element-wise stages of   */
+/* the recurrent flow network, fused.  The convolutions stay on cuDNN.  NHWC     */
+/* ("channels_last") fp32: M = B*H*W pixel rows, channel counts multiples of 4.  */
+/* ------------------------------------------------------------------------- */
+/* ConvGRU.forward (models/submodules.py:134-152) between its convolutions.  zr [M][2C]: output of the merged update|reset
+   convolution on xh, replaced IN PLACE by (z, r) = sigmoid(zr + bias_zr);  xh [M][Cx+C] = (input, previous state);
+   xrh [M][Cx+C] = (input, state * r) -- the input of the candidate convolution (:149) */
+int tef_gru_gates(float *zr, const float *bias_zr, const float *xh, float *xrh, long M, int Cx, int C, void *stream);
+/* c [M][C]: output of the candidate convolution, replaced IN PLACE by cand = tanh(c + bias_c);
+   out [M][C] = state * (1 - z) + cand * z (:150) */
+int tef_gru_output(float *c, const float *bias_c, const float *xh, const float *zr, float *out, long M, int Cx, int C, void *stream);
+/* their reverse, bias gradients included (gbias_* are ADDED to; NULL: skipped).  gout [M][C] ->
+   gc [M][C] (gradient of the candidate convolution's output), gzr[:, :C] (update gate), gh [M][C] = gout * (1 - z) */
+int tef_gru_output_bwd(const float *gout, const float *cand, const float *xh, const float *zr, float *gc, float *gzr, float *gh, float *gbias_c,
+                       float *gbias_zr, long M, int Cx, int C, void *stream);
+/* gxrh [M][Cx+C] (gradient of the candidate convolution's input) -> gzr[:, C:] (reset gate), gh += gxrh[:, Cx:] * r */
+int tef_gru_gates_bwd(const float *gxrh, const float *xh, const float *zr, float *gzr, float *gh, float *gbias_zr, long M, int Cx, int C,
+                      void *stream);
+/* gxh [M][Cx+C] (gradient of the gate convolution's input): gx [M][Cx] = gxrh[:, :Cx] + gxh[:, :Cx];  gh += gxh[:, Cx:] */
+int tef_gru_input_grads(const float *gxrh, const float *gxh, float *gx, float *gh, long M, int Cx, int C, void *stream);
+/* ConvLayer / ResidualBlock (models/submodules.py): y [M][C] = act(y + bias + residual) in place; act 0 none, 1 ReLU, 2 tanh;
+   bias / residual may be NULL */
+int tef_bias_act(float *y, const float *bias, const float *residual, int act, long M, int C, void *stream);
+/* gpre = gy * act'(y) (y = the activated output; gpre may alias gy), gbias [C] += column sums of gpre (NULL: skipped) */
+int tef_bias_act_bwd(const float *gy, const float *y, float *gpre, float *gbias, int act, long M, int C, void *stream);
+/* Flow head (models/model.py:65-85 with train_flow.py:106-108): bilinear up-sampling (align_corners = False) of the 2-channel
+   prediction pred [B][2][h][w] (element strides {batch, channel, row, column}) to out [B][2][H][W] (contiguous), times `scale`
+   (the head's 2^k and flow_scaling in one factor); and its adjoint (deterministic gather) */
+int tef_upsample_scale(const float *pred, const long *strides, int h, int w, float *out, int B, int H, int W, float scale, void *stream);
+int tef_upsample_scale_bwd(const float *gout, int B, int H, int W, float scale, float *gpred, const long *strides, int h, int w, void *stream);
+
 /* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers, 2 = 16-byte gathers,
    4 = 2x2 neighbourhood fetches of tile-sorted positions (mode 0: two 16-byte gathers in the dual-phase layout, 1: one 32-byte gather);
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */

@@ -61,6 +61,50 @@ __device__ __forceinline__ uint32_t warp_chain(const CmParams &p, const float2 *
     uint32_t alive = 0;
     // the event's own location may lie outside the sensor (generic sample); every later position is inside
     const bool in0 = inside(y0, x0, p.res);
+#if TEF_CHAIN_INTERLEAVE
+    // Variant (DESIGN.md decision 21): the forward and the backward chain of an event are independent, so they advance in the
+    // same iteration -- two gathers in flight per thread instead of one.  Dead lanes sample position (0, 0) (a broadcast load)
+    // instead of branching around the sample, so the two samples of an iteration sit in one basic block.
+    if (!QUAD && in0) {
+        float2 qf = make_float2(x0, y0), qb = qf;
+        bool alf = true, alb = true;
+        const float2 *mf = walk_fb + (long)t * stride, *mb = mf;
+        float2 *pwf = pos + (t + 1) * kThreads + threadIdx.x, *pwb = pos + t * kThreads + threadIdx.x;
+        const int nf = p.P - t, nb = t + 1, nc = min(nf, nb);
+        float dtf = (float)(t + 1) - ts, dtb = (float)t - ts;
+        const float2 zero = make_float2(0.f, 0.f);
+        int k = 0;
+        for (; k < nc; ++k, mf += stride, mb -= stride, pwf += kThreads, pwb -= kThreads) {
+            const int trf = t + 1 + k, trb = t - k;
+            const float2 vf = sample_flow_inside_xy<false, false>(mf, p.res, alf ? qf : zero, nullptr);
+            const float2 vb = sample_flow_inside_xy<false, false>(mb, p.res, alb ? qb : zero, nullptr);
+            if (alf) { qf = make_float2(qf.x + dtf * vf.x, qf.y + dtf * vf.y); alf = inside(qf.y, qf.x, p.res); if (alf) alive |= (1u << trf); }
+            if (alb) { qb = make_float2(qb.x + dtb * vb.x, qb.y + dtb * vb.y); alb = inside(qb.y, qb.x, p.res); if (alb) alive |= (1u << trb); }
+            dtf = 1.0f; dtb = -1.0f;
+            if (trf <= keep_hi) { *pwf = qf; if (pb) __stcs(pb + (long)trf * p.rows_grad, qf); }
+            if (trb >= keep_lo) { *pwb = qb; if (pb) __stcs(pb + (long)trb * p.rows_grad, qb); }
+        }
+        for (int kk = k; kk < nf; ++kk, mf += stride, pwf += kThreads) {
+            const int trf = t + 1 + kk;
+            if (alf) {
+                const float2 vf = sample_flow_inside_xy<false, false>(mf, p.res, qf, nullptr);
+                qf = make_float2(qf.x + dtf * vf.x, qf.y + dtf * vf.y); alf = inside(qf.y, qf.x, p.res); if (alf) alive |= (1u << trf);
+            }
+            dtf = 1.0f;
+            if (trf <= keep_hi) { *pwf = qf; if (pb) __stcs(pb + (long)trf * p.rows_grad, qf); }
+        }
+        for (int kk = k; kk < nb; ++kk, mb -= stride, pwb -= kThreads) {
+            const int trb = t - kk;
+            if (alb) {
+                const float2 vb = sample_flow_inside_xy<false, false>(mb, p.res, qb, nullptr);
+                qb = make_float2(qb.x + dtb * vb.x, qb.y + dtb * vb.y); alb = inside(qb.y, qb.x, p.res); if (alb) alive |= (1u << trb);
+            }
+            dtb = -1.0f;
+            if (trb >= keep_lo) { *pwb = qb; if (pb) __stcs(pb + (long)trb * p.rows_grad, qb); }
+        }
+        return alive;
+    }
+#endif
     float2 q = make_float2(x0, y0);
     float tprev = ts;
     bool al = true, safe = in0;

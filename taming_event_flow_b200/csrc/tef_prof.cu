@@ -9,7 +9,7 @@ namespace tef {
 static const char *kNames[K_COUNT] = {
     "stage_events_kernel", "pack_flow_kernel", "unpack_grad_kernel", "iter_fwd_kernel", "iwe_reduce_kernel", "finalize_kernel",
     "iwe_grad_kernel", "iter_bwd_kernel", "sort_hist_kernel", "sort_scan_kernels", "sort_scatter_kernel", "linear_fwd_kernel", "linear_bwd_kernel", "primitive_kernels",
-    "encoding_kernels", "microbench_kernels", "loader_kernels", "validation_kernels", "smoothing_kernels"
+    "encoding_kernels", "microbench_kernels", "loader_kernels", "validation_kernels", "smoothing_kernels", "network_kernels"
 };
 
 struct Pair { cudaEvent_t a, b; int id, dev; };

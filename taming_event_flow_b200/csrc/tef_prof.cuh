@@ -9,7 +9,7 @@ namespace tef {
 
 enum KernelId {
     K_STAGE_EVENTS = 0, K_PACK_FLOW, K_UNPACK_GRAD, K_ITER_FWD, K_IWE_REDUCE, K_FINALIZE, K_IWE_GRAD, K_ITER_BWD,
-    K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER, K_LIN_FWD, K_LIN_BWD, K_PRIMITIVE, K_ENCODING, K_MICROBENCH, K_LOADER, K_VALIDATION, K_SMOOTH, K_COUNT
+    K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER, K_LIN_FWD, K_LIN_BWD, K_PRIMITIVE, K_ENCODING, K_MICROBENCH, K_LOADER, K_VALIDATION, K_SMOOTH, K_NETWORK, K_COUNT
 };
 
 // The event pair lives in the scope itself and joins the pending list only in the destructor, so a concurrent

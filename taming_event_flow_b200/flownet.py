@@ -16,6 +16,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import netops
+
 
 def _conv(cin, cout, k, stride=1, w_scale=None):
     conv = nn.Conv2d(cin, cout, k, stride, k // 2)
@@ -26,31 +28,44 @@ def _conv(cin, cout, k, stride=1, w_scale=None):
 
 
 class ConvGRUCell(nn.Module):
-    def __init__(self, channels):
+    """Upstream's ConvGRU (``models/submodules.py:111-152``) with the update and the reset gate in ONE convolution
+    (``gate_zr``: filters of the update gate stacked over those of the reset gate, each block initialised orthogonally like
+    upstream's separate gates) -- same function, same parameter count.  On fp32 CUDA tensors the cell runs through
+    ``netops.conv_gru``: two convolutions and two fused kernels forward, three fused kernels backward."""
+
+    def __init__(self, channels, fused=True):
         super().__init__()
-        self.gate_z, self.gate_r, self.gate_c = (nn.Conv2d(2 * channels, channels, 3, padding=1) for _ in range(3))
-        for g in (self.gate_z, self.gate_r, self.gate_c):
-            nn.init.orthogonal_(g.weight)
-            nn.init.zeros_(g.bias)
+        self.channels, self.fused = channels, fused
+        self.gate_zr = nn.Conv2d(2 * channels, 2 * channels, 3, padding=1)
+        self.gate_c = nn.Conv2d(2 * channels, channels, 3, padding=1)
+        with torch.no_grad():
+            nn.init.orthogonal_(self.gate_zr.weight[:channels])
+            nn.init.orthogonal_(self.gate_zr.weight[channels:])
+            nn.init.orthogonal_(self.gate_c.weight)
+            nn.init.zeros_(self.gate_zr.bias)
+            nn.init.zeros_(self.gate_c.bias)
 
     def forward(self, x, h):
         if h is None:
             h = torch.zeros_like(x)
-        xh = torch.cat([x, h], 1)
-        z = torch.sigmoid(self.gate_z(xh))
-        r = torch.sigmoid(self.gate_r(xh))
+        if self.fused and netops.usable(x, h):
+            return netops.conv_gru(x, h, self.gate_zr.weight, self.gate_zr.bias, self.gate_c.weight, self.gate_c.bias)
+        z, r = torch.sigmoid(self.gate_zr(torch.cat([x, h], 1))).chunk(2, 1)
         cand = torch.tanh(self.gate_c(torch.cat([x, h * r], 1)))
         return h * (1 - z) + cand * z
 
 
 class RecEVFlowNet(nn.Module):
-    def __init__(self, num_bins=2, base_channels=64, num_encoders=4, final_w_scale=0.01, fp32_heads=True):
+    folds_flow_scaling = True         # forward(x, flow_scaling=...) multiplies the flow maps itself
+
+    def __init__(self, num_bins=2, base_channels=64, num_encoders=4, final_w_scale=0.01, fp32_heads=True, fused=True):
         super().__init__()
         self.fp32_heads = fp32_heads      # under autocast: 1x1 flow heads, tanh and up-sampling in fp32 (bf16 would quantise the flow to 0.4 %)
+        self.fused = fused                # fp32 CUDA tensors go through the fused element-wise kernels of netops (csrc/tef_net.cu)
         chans = [base_channels * 2 ** i for i in range(num_encoders)]            # 64 128 256 512
         ins = [num_bins] + chans[:-1]
         self.enc_conv = nn.ModuleList([_conv(i, o, 3, stride=2) for i, o in zip(ins, chans)])
-        self.enc_gru = nn.ModuleList([ConvGRUCell(o) for o in chans])
+        self.enc_gru = nn.ModuleList([ConvGRUCell(o, fused) for o in chans])
         self.res = nn.ModuleList([nn.ModuleList([_default_conv(chans[-1]), _default_conv(chans[-1])]) for _ in range(2)])
         dec_in = list(reversed(chans))                                           # 512 256 128 64
         dec_out = [c // 2 for c in dec_in]                                       # 256 128 64 32
@@ -65,30 +80,46 @@ class RecEVFlowNet(nn.Module):
     def detach_states(self):
         self.states = [None if s is None else s.detach() for s in self.states]
 
-    def forward(self, x):
+    def _conv_act(self, conv, x, act="relu", residual=None):
+        """act(conv(x) + residual): one cuDNN convolution + one fused kernel (bias, residual, activation) where netops applies."""
+        if self.fused and conv.out_channels % 4 == 0 and netops.usable(residual) and netops.usable_input(x):
+            return netops.conv_bias_act(x, conv.weight, conv.bias, residual, act, conv.stride[0], conv.padding[0])
+        y = conv(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if act == "relu" else (torch.tanh(y) if act == "tanh" else y)
+
+    def _head(self, i, x, size, scale):
+        """1x1 flow head + tanh, up-sampled to the input size and scaled (models/model.py:65-85): returns (prediction, flow map)."""
+        if self.fp32_heads and torch.is_autocast_enabled(x.device.type):
+            with torch.autocast(x.device.type, enabled=False):
+                pred = torch.tanh(self.heads[i](x.float()))
+                return pred, F.interpolate(pred, size=size, mode="bilinear", align_corners=False) * scale
+        pred = torch.tanh(self.heads[i](x))
+        if self.fused and pred.is_cuda and pred.dtype == torch.float32 and not torch.is_autocast_enabled("cuda"):
+            return pred, netops.upsample_scale(pred, size, scale)
+        return pred, F.interpolate(pred, size=size, mode="bilinear", align_corners=False) * scale
+
+    def forward(self, x, flow_scaling=1.0):
+        """`flow_scaling`: extra factor folded into the flow maps (upstream multiplies the network output by
+        config["loss"]["flow_scaling"] in the training loop, train_flow.py:106-108)."""
         H, W = x.shape[2], x.shape[3]
         skips = []
         for i in range(self.num_encoders):
-            x = torch.relu(self.enc_conv[i](x))
+            x = self._conv_act(self.enc_conv[i], x)
             x = self.enc_gru[i](x, self.states[i])
             self.states[i] = x
             skips.append(x)
         for c1, c2 in self.res:
-            x = torch.relu(x + c2(torch.relu(c1(x))))
+            x = self._conv_act(c2, self._conv_act(c1, x), residual=x)
         flows, pred = [], None
         for i in range(self.num_encoders):
             x = x + skips[self.num_encoders - 1 - i]
             if pred is not None:
                 x = torch.cat([pred, x], 1)
-            x = torch.relu(self.dec[i](F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)))
-            if self.fp32_heads and torch.is_autocast_enabled(x.device.type):
-                with torch.autocast(x.device.type, enabled=False):
-                    pred = torch.tanh(self.heads[i](x.float()))
-                    up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
-            else:
-                pred = torch.tanh(self.heads[i](x))
-                up = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=False)
-            flows.append(up * float(2 ** (self.num_encoders - 1 - i)))
+            x = self._conv_act(self.dec[i], F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+            pred, flow = self._head(i, x, (H, W), float(2 ** (self.num_encoders - 1 - i)) * float(flow_scaling))
+            flows.append(flow)
         return {"flow": flows}
 
 

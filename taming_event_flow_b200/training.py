@@ -147,12 +147,14 @@ def _forward_window(model, loss_fn, windows, flow_scaling, encode, autocast):
             x = encode(ev, dev)
         else:
             x = events_to_channels_batched(torch.cat([ev, dev], 1) if dev.shape[1] else ev, res)
+        # px / input window (train_flow.py:107-108); RecEVFlowNet folds the factor into its flow heads
+        folds = getattr(model, "folds_flow_scaling", False)
         if autocast is not None:
             with torch.autocast("cuda", dtype=autocast):
-                out = model(x)["flow"]
-            flows = [f.float() * flow_scaling for f in out]          # the CM loss is fp32 whatever the network computes in
+                out = (model(x, flow_scaling=flow_scaling) if folds else model(x))["flow"]
+            flows = [f.float() if folds else f.float() * flow_scaling for f in out]    # the CM loss is fp32 whatever the network computes in
         else:
-            flows = [f * flow_scaling for f in model(x)["flow"]]     # px / input window (train_flow.py:107-108)
+            flows = model(x, flow_scaling=flow_scaling)["flow"] if folds else [f * flow_scaling for f in model(x)["flow"]]
         loss_fn.update(flows, ev, mk, dev, dmk)
     return loss_fn()
 

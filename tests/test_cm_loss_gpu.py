@@ -651,8 +651,11 @@ def test_graphed_loss_window_replays_the_eager_result():
 
 
 def test_graphed_train_step_follows_the_eager_step():
-    """training.GraphedTrainStep (forward over P windows + CM loss + backward as one CUDA graph, flat gradients, eager clip + Adam)
-    against the eager train_step from the same initial weights: same loss trajectory."""
+    """training.GraphedTrainStep (forward over P windows + CM loss + backward as one CUDA graph, flat gradients, eager clip + optimizer)
+    against the eager train_step from the same initial weights: same loss trajectory (the recurrent states carried from step to step
+    move the loss by percents, the weights by a little).  Plain SGD with a small rate: at training-size steps two EAGER runs of this
+    problem drift apart by 5e-3 within three steps (tests/tools/diag_graph_step.py: the order of the atomic sums differs at 1e-7 and
+    the dynamics amplify it a thousandfold per step), and Adam turns rounding-level gradients into full steps."""
     from taming_event_flow_b200.flownet import RecEVFlowNet
     from taming_event_flow_b200.loss.flow import Iterative
     from taming_event_flow_b200.training import GradReducer, GraphedTrainStep, train_step
@@ -664,7 +667,7 @@ def test_graphed_train_step_follows_the_eager_step():
     for mode in ("eager", "graph"):
         torch.manual_seed(0)
         model = RecEVFlowNet(num_bins=2, base_channels=8).cuda()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-5)
         red = GradReducer(list(model.parameters()), world_size=1)
         loss_fn = Iterative(syn.loss_config(H, W, B, P), "cuda")
         losses = []
@@ -677,5 +680,6 @@ def test_graphed_train_step_follows_the_eager_step():
             losses = [None, None] + [g.step().item() for _ in range(3)]
         out[mode] = losses
     assert all(np.isfinite(out["eager"]))
+    assert abs(out["eager"][3] - out["eager"][2]) > 1e-3 * abs(out["eager"][2]), out["eager"]          # the carried states do matter
     for a, b in zip(out["eager"][2:], out["graph"][2:]):
-        assert abs(a - b) <= 2e-3 * abs(a), (out["eager"], out["graph"])
+        assert abs(a - b) <= 2e-4 * abs(a), (out["eager"], out["graph"])
