@@ -311,6 +311,14 @@ int tef_bias_act_bwd(const float *gy, const float *y, float *gpre, float *gbias,
 int tef_upsample_scale(const float *pred, const long *strides, int h, int w, float *out, int B, int H, int W, float scale, void *stream);
 int tef_upsample_scale_bwd(const float *gout, int B, int H, int W, float scale, float *gpred, const long *strides, int h, int w, void *stream);
 
+/* Decoder stage input (models/arch.py, the decoder loop of the recurrent U-Net): out [B][H][W][Cp] = bilinear up-sampling
+   (align_corners = False; H/h, W/w up to 2.5) of cat(pred, x + skip): x, skip [B][h][w][C] NHWC (skip may be NULL, C even), pred
+   [B][2][h][w] through element strides {batch, channel, row, column} or NULL (then Cp = C, else C + 2); and the adjoint:
+   gout -> gx [B][h][w][C] (the gradient of x and of skip alike) and gpred (pred's strides; NULL when there was no pred) */
+int tef_decoder_up(const float *x, const float *skip, const float *pred, const long *pred_strides, float *out, int B, int h, int w, int C, int H,
+                   int W, void *stream);
+int tef_decoder_up_bwd(const float *gout, float *gx, float *gpred, const long *pred_strides, int B, int h, int w, int C, int H, int W, void *stream);
+
 /* L2 rate micro-benchmarks (what bounds the CM kernels): kind 0 = red.global.add.v4.f32, 1 = 8-byte gathers, 2 = 16-byte gathers,
    4 = 2x2 neighbourhood fetches of tile-sorted positions (mode 0: two 16-byte gathers in the dual-phase layout, 1: one 32-byte gather);
    mode 0 = uniformly random addresses, 1 = a 4 KB window per warp; buf = `bytes` (power of two) of device memory */

@@ -276,6 +276,88 @@ __global__ void __launch_bounds__(kNetThreads) upsample_scale_bwd_kernel(const f
     if (live && lane == 0) gpred[(bc >> 1) * sb + (bc & 1) * sc + i * sy + j * sx] = acc * scale;
 }
 
+// ---- decoder stage input (models/arch.py decoder loop): (x + skip), the previous flow prediction concatenated in front, and the
+// bilinear x2 up-sampling that precedes the decoder's convolution -- one kernel instead of add, cat and up-sample ----------------
+// x, skip: [B][h][w][C] (NHWC);  pred: [B][2][h][w] through element strides, or NULL;  out: [B][H][W][Cp], Cp = C + (pred ? 2 : 0).
+// One thread per output pixel and channel PAIR (C is even; Cp = 66, 130, 258 are not multiples of four).
+__global__ void __launch_bounds__(kNetThreads) decoder_up_kernel(const float *__restrict__ x, const float *__restrict__ skip, const float *__restrict__ pred,
+                                                                 long sb, long sc, long sy, long sx, float *__restrict__ out, int B, int h, int w, int C,
+                                                                 int H, int W) {
+    const int np = pred ? 1 : 0, Cp2 = (C >> 1) + np;
+    const long n = (long)B * H * W * Cp2;
+    const float rh = (float)h / (float)H, rw = (float)w / (float)W;
+    for (long i = (long)blockIdx.x * kNetThreads + threadIdx.x; i < n; i += (long)gridDim.x * kNetThreads) {
+        const int c2 = (int)(i % Cp2);
+        const long pix = i / Cp2;
+        const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+        const long b = pix / ((long)W * H);
+        const UpIdx uy = up_index(Y, rh, h), ux = up_index(X, rw, w);
+        float2 v[4];
+        if (c2 < np) {
+            const float *p = pred + b * sb;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long o = (long)((k >> 1) ? uy.i1 : uy.i0) * sy + (long)((k & 1) ? ux.i1 : ux.i0) * sx;
+                v[k] = make_float2(__ldg(p + o), __ldg(p + o + sc));
+            }
+        } else {
+            const int c = 2 * (c2 - np);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long o = ((b * h + ((k >> 1) ? uy.i1 : uy.i0)) * w + ((k & 1) ? ux.i1 : ux.i0)) * C + c;
+                v[k] = *reinterpret_cast<const float2 *>(x + o);
+                if (skip) { const float2 s2 = *reinterpret_cast<const float2 *>(skip + o); v[k].x += s2.x; v[k].y += s2.y; }
+            }
+        }
+        float2 r;
+        r.x = uy.l0 * (ux.l0 * v[0].x + ux.l1 * v[1].x) + uy.l1 * (ux.l0 * v[2].x + ux.l1 * v[3].x);
+        r.y = uy.l0 * (ux.l0 * v[0].y + ux.l1 * v[1].y) + uy.l1 * (ux.l0 * v[2].y + ux.l1 * v[3].y);
+        *reinterpret_cast<float2 *>(out + 2 * i) = r;
+    }
+}
+// adjoint (deterministic gather): one thread per low-resolution pixel and channel pair; the 1-D weights of the candidate output
+// rows / columns are derived once, then the non-zero ones are walked.  gx receives the gradient of x and of skip alike.
+constexpr int kUpWin = 8;          // candidate output rows per input row: 2 * scale + 3 <= 8 covers scale factors up to 2.5
+__global__ void __launch_bounds__(kNetThreads) decoder_up_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float *__restrict__ gpred,
+                                                                     long sb, long sc, long sy, long sx, int B, int h, int w, int C, int H, int W) {
+    const int np = gpred ? 1 : 0, Cp2 = (C >> 1) + np, Cp = 2 * Cp2;
+    const long n = (long)B * h * w * Cp2;
+    const float rh = (float)h / (float)H, rw = (float)w / (float)W;
+    for (long idx = (long)blockIdx.x * kNetThreads + threadIdx.x; idx < n; idx += (long)gridDim.x * kNetThreads) {
+        const int c2 = (int)(idx % Cp2);
+        const long pix = idx / Cp2;
+        const int j = (int)(pix % w), i = (int)((pix / w) % h);
+        const long b = pix / ((long)w * h);
+        const int y_lo = max(0, (int)floorf(((float)i - 0.5f) / rh - 0.5f) - 1), x_lo = max(0, (int)floorf(((float)j - 0.5f) / rw - 0.5f) - 1);
+        float wy[kUpWin], wx[kUpWin];
+#pragma unroll
+        for (int k = 0; k < kUpWin; ++k) {
+            const int y = y_lo + k, xx = x_lo + k;
+            wy[k] = 0.0f; wx[k] = 0.0f;
+            if (y < H) { const UpIdx u = up_index(y, rh, h); wy[k] = (u.i0 == i ? u.l0 : 0.0f) + (u.i1 == i ? u.l1 : 0.0f); }
+            if (xx < W) { const UpIdx u = up_index(xx, rw, w); wx[k] = (u.i0 == j ? u.l0 : 0.0f) + (u.i1 == j ? u.l1 : 0.0f); }
+        }
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < kUpWin; ++ky) {
+            if (wy[ky] == 0.0f) continue;
+#pragma unroll
+            for (int kx = 0; kx < kUpWin; ++kx) {
+                if (wx[kx] == 0.0f) continue;
+                const float2 g = *reinterpret_cast<const float2 *>(gout + ((b * H + y_lo + ky) * W + x_lo + kx) * Cp + 2 * c2);
+                const float wgt = wy[ky] * wx[kx];
+                acc.x += wgt * g.x; acc.y += wgt * g.y;
+            }
+        }
+        if (c2 < np) {
+            float *p = gpred + b * sb + (long)i * sy + (long)j * sx;
+            p[0] = acc.x; p[sc] = acc.y;
+        } else {
+            *reinterpret_cast<float2 *>(gx + ((b * h + i) * w + j) * C + 2 * (c2 - np)) = acc;
+        }
+    }
+}
+
 static int grid_for(long n) {
     long nb = (n + kNetThreads - 1) / kNetThreads;
     if (nb > 148 * 8) nb = 148 * 8;
@@ -359,5 +441,26 @@ extern "C" int tef_upsample_scale_bwd(const float *gout, int B, int H, int W, fl
     if (lpe == 1) upsample_scale_bwd_kernel<1><<<nb, kNetThreads, 0, st>>>(gout, B, H, W, scale, gpred, strides[0], strides[1], strides[2], strides[3], h, w);
     else if (lpe == 8) upsample_scale_bwd_kernel<8><<<nb, kNetThreads, 0, st>>>(gout, B, H, W, scale, gpred, strides[0], strides[1], strides[2], strides[3], h, w);
     else upsample_scale_bwd_kernel<32><<<nb, kNetThreads, 0, st>>>(gout, B, H, W, scale, gpred, strides[0], strides[1], strides[2], strides[3], h, w);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_decoder_up(const float *x, const float *skip, const float *pred, const long *pred_strides, float *out, int B, int h, int w, int C,
+                              int H, int W, void *stream) {
+    if (!x || !out || B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || C < 2 || (C & 1) || (pred && !pred_strides)) return TEF_EINVAL;
+    const long z[4] = { 0, 0, 0, 0 };
+    const long *ps = pred ? pred_strides : z;
+    ProfScope ps_(K_NETWORK, (cudaStream_t)stream);
+    decoder_up_kernel<<<grid_for((long)B * H * W * ((C >> 1) + (pred ? 1 : 0))), kNetThreads, 0, (cudaStream_t)stream>>>(x, skip, pred, ps[0], ps[1], ps[2], ps[3],
+                                                                                                                     out, B, h, w, C, H, W);
+    return (int)cudaGetLastError();
+}
+extern "C" int tef_decoder_up_bwd(const float *gout, float *gx, float *gpred, const long *pred_strides, int B, int h, int w, int C, int H, int W,
+                                  void *stream) {
+    if (!gout || !gx || B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || C < 2 || (C & 1) || (gpred && !pred_strides)) return TEF_EINVAL;
+    if ((float)H / (float)h * 2.0f + 3.0f > (float)kUpWin || (float)W / (float)w * 2.0f + 3.0f > (float)kUpWin) return TEF_ELIMIT;
+    const long z[4] = { 0, 0, 0, 0 };
+    const long *ps = gpred ? pred_strides : z;
+    ProfScope ps_(K_NETWORK, (cudaStream_t)stream);
+    decoder_up_bwd_kernel<<<grid_for((long)B * h * w * ((C >> 1) + (gpred ? 1 : 0))), kNetThreads, 0, (cudaStream_t)stream>>>(gout, gx, gpred, ps[0], ps[1], ps[2],
+                                                                                                                          ps[3], B, h, w, C, H, W);
     return (int)cudaGetLastError();
 }

@@ -36,6 +36,7 @@ class ConvGRUCell(nn.Module):
     def __init__(self, channels, fused=True):
         super().__init__()
         self.channels, self.fused = channels, fused
+        self.stacks = netops.WindowStacks()       # deferred weight gradient over a loss window (RecEVFlowNet.begin_window)
         self.gate_zr = nn.Conv2d(2 * channels, 2 * channels, 3, padding=1)
         self.gate_c = nn.Conv2d(2 * channels, channels, 3, padding=1)
         with torch.no_grad():
@@ -49,7 +50,7 @@ class ConvGRUCell(nn.Module):
         if h is None:
             h = torch.zeros_like(x)
         if self.fused and netops.usable(x, h):
-            return netops.conv_gru(x, h, self.gate_zr.weight, self.gate_zr.bias, self.gate_c.weight, self.gate_c.bias)
+            return netops.conv_gru(x, h, self.gate_zr.weight, self.gate_zr.bias, self.gate_c.weight, self.gate_c.bias, self.stacks)
         z, r = torch.sigmoid(self.gate_zr(torch.cat([x, h], 1))).chunk(2, 1)
         cand = torch.tanh(self.gate_c(torch.cat([x, h * r], 1)))
         return h * (1 - z) + cand * z
@@ -73,6 +74,17 @@ class RecEVFlowNet(nn.Module):
         self.heads = nn.ModuleList([_conv(o, 2, 1, w_scale=final_w_scale) for o in dec_out])
         self.num_encoders = num_encoders
         self.states = [None] * num_encoders
+        # deferred weight gradients over a loss window (begin_window): one WindowStacks per convolution the fused path runs
+        self._stacks = {id(c): netops.WindowStacks() for c in list(self.enc_conv) + [c for pair in self.res for c in pair] + list(self.dec)}
+
+    def begin_window(self, passes):
+        """Open a loss window of `passes` forward calls whose loss back-propagates through all of them (upstream's training loop,
+        train_flow.py:106-137): the recurrent layers then compute their weight gradients once per window instead of once per
+        pass (netops.WindowStacks).  `passes` = 0 switches back to per-pass gradients."""
+        for cell in self.enc_gru:
+            cell.stacks.begin(passes if self.fused else 0)
+        for st in self._stacks.values():
+            st.begin(passes if self.fused else 0)
 
     def reset_states(self):
         self.states = [None] * self.num_encoders
@@ -80,10 +92,10 @@ class RecEVFlowNet(nn.Module):
     def detach_states(self):
         self.states = [None if s is None else s.detach() for s in self.states]
 
-    def _conv_act(self, conv, x, act="relu", residual=None):
+    def _conv_act(self, conv, x, act="relu", residual=None, slot=None):
         """act(conv(x) + residual): one cuDNN convolution + one fused kernel (bias, residual, activation) where netops applies."""
         if self.fused and conv.out_channels % 4 == 0 and netops.usable(residual) and netops.usable_input(x):
-            return netops.conv_bias_act(x, conv.weight, conv.bias, residual, act, conv.stride[0], conv.padding[0])
+            return netops.conv_bias_act(x, conv.weight, conv.bias, residual, act, conv.stride[0], conv.padding[0], self._stacks.get(id(conv)), slot)
         y = conv(x)
         if residual is not None:
             y = y + residual
@@ -114,10 +126,23 @@ class RecEVFlowNet(nn.Module):
             x = self._conv_act(c2, self._conv_act(c1, x), residual=x)
         flows, pred = [], None
         for i in range(self.num_encoders):
-            x = x + skips[self.num_encoders - 1 - i]
-            if pred is not None:
-                x = torch.cat([pred, x], 1)
-            x = self._conv_act(self.dec[i], F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+            skip = skips[self.num_encoders - 1 - i]
+            slot = None
+            if self.fused and netops.usable(x, skip) and (pred is None or pred.dtype == torch.float32):
+                # skip sum, concatenation and x2 up-sampling in one kernel, written straight into the decoder convolution's slot
+                conv, st = self.dec[i], self._stacks[id(self.dec[i])]
+                slot = st.take_slot() if conv.out_channels % 4 == 0 else None        # (else the convolution runs unfused)
+                out = None
+                if slot is not None:
+                    shp = (x.shape[0], x.shape[1] + (2 if pred is not None else 0), 2 * x.shape[2], 2 * x.shape[3])
+                    out = netops.conv_input_slot(st, slot, shp, conv.weight, conv.stride[0], conv.padding[0], x.device)
+                x = netops.decoder_up(x, skip, pred, 2, out=out)
+            else:
+                x = x + skip
+                if pred is not None:
+                    x = torch.cat([pred, x], 1)
+                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+            x = self._conv_act(self.dec[i], x, slot=slot)
             pred, flow = self._head(i, x, (H, W), float(2 ** (self.num_encoders - 1 - i)) * float(flow_scaling))
             flows.append(flow)
         return {"flow": flows}

@@ -55,95 +55,207 @@ def _conv_bwd(g, x, w, stride, padding, need_x=True):
     return gx, gw
 
 
-class _FusedConvGRU(torch.autograd.Function):
-    """new_state = ConvGRU(x, h) with the update and reset gates merged into one convolution (w_zr = [w_update; w_reset])."""
+def _conv_bwd_input(g, x, w, stride, padding):
+    return torch.ops.aten.convolution_backward(g, x, w, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+
+
+def _conv_bwd_weight(g, x, w, stride, padding):
+    return torch.ops.aten.convolution_backward(g, x, w, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+
+
+class WindowStacks:
+    """Per-layer storage of one loss window for the DEFERRED weight gradient (back-propagation through time).
+
+    A recurrent step re-uses every filter in each of the P passes of a loss window, and autograd computes one small weight
+    gradient per pass and sums them (P launches of a skinny GEMM whose reduction dimension is one pass's B*H*W pixels, P - 1
+    additions of the full filter bank).  The weight gradient is linear in (input, output gradient) pairs, so the fused
+    operators keep the convolution inputs and the output gradients of all passes side by side -- `x[name]` and `g[name]` are
+    [P*B, C, H, W] channels_last stacks, pass t in rows t*B..(t+1)*B, written in place by the kernels that produce them -- and
+    the backward of the window's FIRST pass (the last to run) computes ONE weight gradient over all of them.
+    Requires the loss to back-propagate through every pass down to the first, which is what upstream's training loop does
+    (``train_flow.py:106-137``); `begin(P)` opts a window in, a layer called more often than P times falls back to the
+    per-pass gradient."""
+
+    def __init__(self):
+        self.P, self.slot, self.used, self.key, self.x, self.g = 0, 0, 0, None, {}, {}
+
+    def begin(self, P):
+        self.P, self.slot, self.used = int(P), 0, 0
+
+    def take_slot(self):
+        """Slot of this forward call, or None when the window is not open / already full / gradients are off."""
+        if self.P <= 0 or self.slot >= self.P or not torch.is_grad_enabled():
+            return None
+        t = self.slot
+        self.slot += 1
+        self.used = max(self.used, self.slot)
+        return t
+
+    def ensure(self, key, shapes_x, shapes_g, device):
+        """(Re)allocate the stacks: shapes_* = {name: (B, C, H, W)} of one pass."""
+        key = (self.P, key)
+        if key != self.key:
+            mk = lambda shp: torch.empty((self.P * shp[0],) + tuple(shp[1:]), dtype=torch.float32, device=device, memory_format=CL)
+            self.x = {k: mk(v) for k, v in shapes_x.items()}
+            self.g = {k: mk(v) for k, v in shapes_g.items()}
+            self.key = key
 
     @staticmethod
-    def forward(ctx, x, h, w_zr, b_zr, w_c, b_c):
+    def rows(stack, t, B):
+        return stack[t * B:(t + 1) * B]
+
+
+class _FusedConvGRU(torch.autograd.Function):
+    """new_state = ConvGRU(x, h) with the update and reset gates merged into one convolution (w_zr = [w_update; w_reset]).
+    With `stacks` / `slot` (WindowStacks) the weight gradients of the window are computed once, by the first pass's backward."""
+
+    @staticmethod
+    def forward(ctx, x, h, w_zr, b_zr, w_c, b_c, stacks, slot):
         L = _lib.lib()
         st = _lib.stream()
-        Cx, C = x.shape[1], h.shape[1]
+        B, Cx, H, W = x.shape
+        C = h.shape[1]
         pad = w_zr.shape[2] // 2
-        xh = _cl(torch.cat([_cl(x), _cl(h)], 1))
-        M = _rows(xh)
+        M = B * H * W
+        if slot is not None:
+            stacks.ensure(("gru", B, Cx, C, H, W), {"xh": (B, Cx + C, H, W), "xrh": (B, Cx + C, H, W)}, {"zr": (B, 2 * C, H, W), "c": (B, C, H, W)}, x.device)
+            xh, xrh = stacks.rows(stacks.x["xh"], slot, B), stacks.rows(stacks.x["xrh"], slot, B)
+            torch.cat([x, h], 1, out=xh)
+        else:
+            xh = _cl(torch.cat([_cl(x), _cl(h)], 1))
+            xrh = torch.empty_like(xh)
         zr = _conv(xh, w_zr, 1, pad)
-        xrh = torch.empty_like(xh)
         _lib.check(L.tef_gru_gates(_lib.ptr(zr), _lib.ptr(b_zr), _lib.ptr(xh), _lib.ptr(xrh), ctypes.c_long(M), Cx, C, st), "tef_gru_gates")
         c = _conv(xrh, w_c, 1, pad)
         out = torch.empty_like(c)
         _lib.check(L.tef_gru_output(_lib.ptr(c), _lib.ptr(b_c), _lib.ptr(xh), _lib.ptr(zr), _lib.ptr(out), ctypes.c_long(M), Cx, C, st), "tef_gru_output")
-        ctx.save_for_backward(xh, xrh, zr, c, w_zr, w_c)
-        ctx.dims = (M, Cx, C, pad, b_zr is not None, b_c is not None)
+        # plain attributes, not save_for_backward: the stack slots are views of a buffer the other passes write to
+        ctx.t = (xh, xrh, zr, c, w_zr, w_c)
+        ctx.dims = (M, B, Cx, C, pad, b_zr is not None, b_c is not None, stacks, slot)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
-        xh, xrh, zr, cand, w_zr, w_c = ctx.saved_tensors
-        M, Cx, C, pad, has_bzr, has_bc = ctx.dims
+        xh, xrh, zr, cand, w_zr, w_c = ctx.t
+        M, B, Cx, C, pad, has_bzr, has_bc, stacks, slot = ctx.dims
         L = _lib.lib()
         st = _lib.stream()
         gout = _cl(gout)
-        gc, gzr, gh = torch.empty_like(cand), torch.empty_like(zr), torch.empty_like(cand)
+        if slot is not None:
+            gc, gzr = stacks.rows(stacks.g["c"], slot, B), stacks.rows(stacks.g["zr"], slot, B)
+        else:
+            gc, gzr = torch.empty_like(cand), torch.empty_like(zr)
+        gh = torch.empty_like(cand)
         gb = torch.zeros(3 * C, dtype=torch.float32, device=gout.device)
         gb_zr, gb_c = gb[:2 * C], gb[2 * C:]
         _lib.check(L.tef_gru_output_bwd(_lib.ptr(gout), _lib.ptr(cand), _lib.ptr(xh), _lib.ptr(zr), _lib.ptr(gc), _lib.ptr(gzr), _lib.ptr(gh),
                                         _lib.ptr(gb_c) if has_bc else None, _lib.ptr(gb_zr) if has_bzr else None, ctypes.c_long(M), Cx, C, st),
                    "tef_gru_output_bwd")
-        gxrh, gw_c = _conv_bwd(gc, xrh, w_c, 1, pad)
+        gw_c = gw_zr = None
+        if slot is None:
+            gxrh, gw_c = _conv_bwd(gc, xrh, w_c, 1, pad)
+        else:
+            gxrh = _conv_bwd_input(gc, xrh, w_c, 1, pad)
         gxrh = _cl(gxrh)
         _lib.check(L.tef_gru_gates_bwd(_lib.ptr(gxrh), _lib.ptr(xh), _lib.ptr(zr), _lib.ptr(gzr), _lib.ptr(gh), _lib.ptr(gb_zr) if has_bzr else None,
                                        ctypes.c_long(M), Cx, C, st), "tef_gru_gates_bwd")
-        gxh, gw_zr = _conv_bwd(gzr, xh, w_zr, 1, pad)
+        if slot is None:
+            gxh, gw_zr = _conv_bwd(gzr, xh, w_zr, 1, pad)
+        else:
+            gxh = _conv_bwd_input(gzr, xh, w_zr, 1, pad)
         gxh = _cl(gxh)
-        gx = torch.empty((xh.shape[0], Cx, xh.shape[2], xh.shape[3]), dtype=torch.float32, device=gout.device, memory_format=CL)
+        gx = torch.empty((B, Cx, xh.shape[2], xh.shape[3]), dtype=torch.float32, device=gout.device, memory_format=CL)
         _lib.check(L.tef_gru_input_grads(_lib.ptr(gxrh), _lib.ptr(gxh), _lib.ptr(gx), _lib.ptr(gh), ctypes.c_long(M), Cx, C, st), "tef_gru_input_grads")
-        return gx, gh, gw_zr, (gb_zr if has_bzr else None), gw_c, (gb_c if has_bc else None)
+        if slot == 0:                                           # the window's first pass: every pair of the window is in the stacks
+            n = stacks.used * B
+            gw_c = _conv_bwd_weight(stacks.g["c"][:n], stacks.x["xrh"][:n], w_c, 1, pad)
+            gw_zr = _conv_bwd_weight(stacks.g["zr"][:n], stacks.x["xh"][:n], w_zr, 1, pad)
+        ctx.t = None
+        return gx, gh, gw_zr, (gb_zr if has_bzr else None), gw_c, (gb_c if has_bc else None), None, None
 
 
-def conv_gru(x, h, w_zr, b_zr, w_c, b_c):
+def conv_gru(x, h, w_zr, b_zr, w_c, b_c, stacks=None):
     """ConvGRU cell (upstream ``models/submodules.py:134-152``): z, r = sigmoid(conv_zr([x, h])); cand = tanh(conv_c([x, h * r]));
-    returns h * (1 - z) + cand * z.  `w_zr` stacks the update gate's filters over the reset gate's."""
+    returns h * (1 - z) + cand * z.  `w_zr` stacks the update gate's filters over the reset gate's.  `stacks`: the layer's
+    WindowStacks when the weight gradients of a loss window are to be computed once (see there)."""
     _lib.require_cuda(x, h, w_zr, w_c)
-    return _FusedConvGRU.apply(x, h, w_zr, b_zr, w_c, b_c)
+    slot = stacks.take_slot() if stacks is not None else None
+    return _FusedConvGRU.apply(x, h, w_zr, b_zr, w_c, b_c, stacks if slot is not None else None, slot)
 
 
 class _ConvBiasAct(torch.autograd.Function):
-    """act(conv(x, w) + b + residual); the backward pass forms the activation derivative and the bias gradient in one kernel."""
+    """act(conv(x, w) + b + residual); the backward pass forms the activation derivative and the bias gradient in one kernel.
+    With `stacks` / `slot` the weight gradient of the loss window is computed once, by the first pass's backward (WindowStacks)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, residual, act, stride, padding):
+    def forward(ctx, x, w, b, residual, act, stride, padding, stacks, slot):
         L = _lib.lib()
-        x = _cl(x)
+        B = x.shape[0]
+        if slot is not None:
+            xs = conv_input_slot(stacks, slot, x.shape, w, stride, padding, x.device)
+            if xs.data_ptr() != x.data_ptr() or xs.stride() != x.stride():
+                xs.copy_(x)                       # producers that know their consumer write the slot themselves (decoder_up(out=...))
+            x = xs
+        else:
+            x = _cl(x)
         y = _conv(x, w, stride, padding)
         res = _cl(residual) if residual is not None else None
         M, C = _rows(y), y.shape[1]
         _lib.check(L.tef_bias_act(_lib.ptr(y), _lib.ptr(b), _lib.ptr(res), act, ctypes.c_long(M), C, _lib.stream()), "tef_bias_act")
-        ctx.save_for_backward(x, w, y)
-        ctx.cfg = (act, stride, padding, b is not None, residual is not None, M, C)
+        ctx.t = (x, w, y)
+        ctx.cfg = (act, stride, padding, b is not None, residual is not None, M, C, B, stacks, slot)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
-        act, stride, padding, has_b, has_res, M, C = ctx.cfg
+        x, w, y = ctx.t
+        act, stride, padding, has_b, has_res, M, C, B, stacks, slot = ctx.cfg
         L = _lib.lib()
         gy = _cl(gy)
-        gpre = torch.empty_like(gy) if act else gy
+        if slot is not None:
+            gpre = stacks.rows(stacks.g["y"], slot, B)
+        else:
+            gpre = torch.empty_like(gy) if act else gy
         gb = torch.zeros(C, dtype=torch.float32, device=gy.device) if has_b else None
         if act or has_b:
             _lib.check(L.tef_bias_act_bwd(_lib.ptr(gy), _lib.ptr(y), _lib.ptr(gpre), _lib.ptr(gb), act, ctypes.c_long(M), C, _lib.stream()), "tef_bias_act_bwd")
-        gx, gw = _conv_bwd(gpre, x, w, stride, padding, need_x=ctx.needs_input_grad[0])
-        return gx, gw, gb, (gpre if has_res else None), None, None, None
+        elif slot is not None:
+            gpre.copy_(gy)
+        gx = gw = None
+        if slot is None:
+            gx, gw = _conv_bwd(gpre, x, w, stride, padding, need_x=ctx.needs_input_grad[0])
+        else:
+            if ctx.needs_input_grad[0]:
+                gx = _conv_bwd_input(gpre, x, w, stride, padding)
+            if slot == 0:
+                n = stacks.used * B
+                gw = _conv_bwd_weight(stacks.g["y"][:n], stacks.x["x"][:n], w, stride, padding)
+        ctx.t = None
+        # the residual's gradient must not alias a stack slot the next window overwrites while autograd may still hold it
+        return gx, gw, gb, ((gpre.clone() if slot is not None else gpre) if has_res else None), None, None, None, None, None
 
 
-def conv_bias_act(x, w, b=None, residual=None, act="relu", stride=1, padding=None):
-    """act(conv2d(x, w, stride, padding) + b + residual), channels_last fp32 (ConvLayer / ResidualBlock of upstream's submodules)."""
+def conv_input_slot(stacks, slot, x_shape, w, stride, padding, device):
+    """The [B, Cin, H, W] channels_last view a convolution's input of pass `slot` lives in (allocating the layer's stacks)."""
+    B, Cin, H, W = x_shape
+    k = w.shape[2]
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    stacks.ensure(("conv", B, Cin, H, W, w.shape[0], stride, padding), {"x": (B, Cin, H, W)}, {"y": (B, w.shape[0], Ho, Wo)}, device)
+    return stacks.rows(stacks.x["x"], slot, B)
+
+
+def conv_bias_act(x, w, b=None, residual=None, act="relu", stride=1, padding=None, stacks=None, slot=None):
+    """act(conv2d(x, w, stride, padding) + b + residual), channels_last fp32 (ConvLayer / ResidualBlock of upstream's submodules).
+    `stacks`: the layer's WindowStacks for one weight gradient per loss window; `slot`: a slot already taken from it (by a
+    producer that wrote the input in place), else one is taken here."""
     _lib.require_cuda(x, w)
     if padding is None:
         padding = w.shape[2] // 2
-    return _ConvBiasAct.apply(x, w, b, residual, ACT[act], stride, padding)
+    if stacks is not None and slot is None:
+        slot = stacks.take_slot()
+    return _ConvBiasAct.apply(x, w, b, residual, ACT[act], stride, padding, stacks if slot is not None else None, slot)
 
 
 class _UpsampleScale(torch.autograd.Function):
@@ -182,3 +294,45 @@ def upsample_scale(pred, size, scale):
     if any(s <= 0 for s in dense):                       # expanded / negative strides: materialise
         pred = pred.contiguous()
     return _UpsampleScale.apply(pred, int(size[0]), int(size[1]), float(scale))
+
+
+class _DecoderUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip, pred, scale, out):
+        L = _lib.lib()
+        x = _cl(x)
+        skip = _cl(skip) if skip is not None else None
+        B, C, h, w = x.shape
+        H, W = int(h * scale), int(w * scale)
+        Cp = C + (2 if pred is not None else 0)
+        out = out[0] if out is not None else None         # handed over in a list: a buffer to fill, not an input of the operator
+        if out is None:
+            out = torch.empty((B, Cp, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
+        elif tuple(out.shape) != (B, Cp, H, W) or not out.is_contiguous(memory_format=CL):
+            raise _lib.TefShapeError("decoder_up: out must be a channels_last [%d, %d, %d, %d] tensor" % (B, Cp, H, W))
+        ps = (ctypes.c_long * 4)(*pred.stride()) if pred is not None else None
+        _lib.check(L.tef_decoder_up(_lib.ptr(x), _lib.ptr(skip), _lib.ptr(pred), ps, _lib.ptr(out), B, h, w, C, H, W, _lib.stream()), "tef_decoder_up")
+        ctx.geom = (B, h, w, C, H, W, tuple(pred.stride()) if pred is not None else None, skip is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        B, h, w, C, H, W, pstr, has_skip = ctx.geom
+        L = _lib.lib()
+        g = _cl(g)
+        gx = torch.empty((B, C, h, w), dtype=torch.float32, device=g.device, memory_format=CL)
+        gpred = torch.empty_strided((B, 2, h, w), pstr, dtype=torch.float32, device=g.device) if pstr is not None else None
+        ps = (ctypes.c_long * 4)(*pstr) if pstr is not None else None
+        _lib.check(L.tef_decoder_up_bwd(_lib.ptr(g), _lib.ptr(gx), _lib.ptr(gpred), ps, B, h, w, C, H, W, _lib.stream()), "tef_decoder_up_bwd")
+        return gx, (gx if has_skip else None), gpred, None, None
+
+
+def decoder_up(x, skip=None, pred=None, scale=2, out=None):
+    """``F.interpolate(cat([pred, x + skip], 1), scale_factor=scale, mode="bilinear", align_corners=False)`` in one kernel each way
+    (the input of a decoder stage of upstream's recurrent U-Net, ``models/arch.py``): channels_last fp32, even channel count.
+    `out`: write into this channels_last tensor (the consumer convolution's slot of a WindowStacks) instead of a new one."""
+    _lib.require_cuda(x, skip, pred)
+    if pred is not None and (pred.dim() != 4 or pred.shape[1] != 2 or any(st <= 0 for st in pred.stride())):
+        raise _lib.TefShapeError("decoder_up expects a dense [B, 2, h, w] flow prediction")
+    return _DecoderUp.apply(x, skip, pred, scale, [out] if out is not None else None)

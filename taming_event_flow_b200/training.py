@@ -142,6 +142,8 @@ def _forward_window(model, loss_fn, windows, flow_scaling, encode, autocast):
 
     res = loss_fn.res
     loss_fn.reset()
+    if hasattr(model, "begin_window"):
+        model.begin_window(len(windows))         # one weight gradient per recurrent layer and window (netops.WindowStacks)
     for ev, mk, dev, dmk in windows:
         if encode is not None:
             x = encode(ev, dev)

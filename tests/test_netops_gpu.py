@@ -24,8 +24,9 @@ def _fp32_convs():
     torch.backends.cudnn.allow_tf32 = old
 
 
+@pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("B,C,H,W", [(2, 8, 12, 20), (3, 64, 16, 16), (1, 512, 4, 4), (2, 12, 5, 7)])
-def test_conv_gru_matches_the_module_formulation(B, C, H, W):
+def test_conv_gru_matches_the_module_formulation(B, C, H, W, deferred):
     from taming_event_flow_b200.flownet import ConvGRUCell
 
     torch.manual_seed(C + H)
@@ -39,6 +40,7 @@ def test_conv_gru_matches_the_module_formulation(B, C, H, W):
     res = {}
     for fused in (False, True):
         cell.fused = fused
+        cell.stacks.begin(2 if (fused and deferred) else 0)          # one weight gradient for the two steps (netops.WindowStacks)
         x, h = x0.clone().requires_grad_(True), h0.clone().requires_grad_(True)
         for p in cell.parameters():
             p.grad = None
@@ -97,7 +99,32 @@ def test_upsample_scale_matches_interpolate(h, w, H, W, channels_last):
         assert rel(a, b) < TOL
 
 
-def test_fused_network_matches_the_plain_network_over_a_recurrent_window():
+@pytest.mark.parametrize("B,C,h,w,with_pred,with_skip", [(2, 8, 6, 9, True, True), (1, 64, 16, 16, True, True), (2, 512, 4, 4, False, True), (2, 32, 5, 3, True, False)])
+def test_decoder_up_matches_add_cat_interpolate(B, C, h, w, with_pred, with_skip):
+    from taming_event_flow_b200 import netops
+
+    torch.manual_seed(C)
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    x0, s0, p0 = cl(torch.randn(B, C, h, w, device="cuda")), cl(torch.randn(B, C, h, w, device="cuda")), cl(torch.randn(B, 2, h, w, device="cuda"))
+    g = torch.randn(B, C + (2 if with_pred else 0), 2 * h, 2 * w, device="cuda")
+    out = {}
+    for fused in (False, True):
+        x, sk, pr = x0.clone().requires_grad_(True), s0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+        if fused:
+            y = netops.decoder_up(x, sk if with_skip else None, pr if with_pred else None, 2)
+        else:
+            y = x + sk if with_skip else x
+            if with_pred:
+                y = torch.cat([pr, y], 1)
+            y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=False)
+        (y * g).sum().backward()
+        out[fused] = [y, x.grad] + ([sk.grad] if with_skip else []) + ([pr.grad] if with_pred else [])
+    for a, b in zip(out[True], out[False]):
+        assert rel(a, b) < TOL
+
+
+@pytest.mark.parametrize("window", [0, 3, 2])
+def test_fused_network_matches_the_plain_network_over_a_recurrent_window(window):
     """RecEVFlowNet(fused=True) against fused=False from the same weights: flow maps of three recurrent passes and every parameter
     gradient of a loss on them."""
     from taming_event_flow_b200.flownet import RecEVFlowNet
@@ -117,6 +144,7 @@ def test_fused_network_matches_the_plain_network_over_a_recurrent_window():
             c.fused = fused
         net.reset_states()
         net.zero_grad(set_to_none=True)
+        net.begin_window(window)             # 3: deferred weight gradients over the window; 2: the third pass falls back to its own; 0: off
         loss, flows = 0.0, []
         for x, g in zip(xs, gs):
             fl = net(x, flow_scaling=32.0)["flow"]
