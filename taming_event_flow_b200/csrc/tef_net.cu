@@ -280,41 +280,104 @@ __global__ void __launch_bounds__(kNetThreads) upsample_scale_bwd_kernel(const f
 // bilinear x2 up-sampling that precedes the decoder's convolution -- one kernel instead of add, cat and up-sample ----------------
 // x, skip: [B][h][w][C] (NHWC);  pred: [B][2][h][w] through element strides, or NULL;  out: [B][H][W][Cp], Cp = C + (pred ? 2 : 0).
 // One thread per output pixel and channel PAIR (C is even; Cp = 66, 130, 258 are not multiples of four).
+// One CTA per output row (b, Y): 32 lanes walk the channel pairs of a pixel (coalesced 256-byte runs), 8 pixel lanes walk
+// the row -- no integer division anywhere (the flat-index version spent its time in 64-bit div / mod).
 __global__ void __launch_bounds__(kNetThreads) decoder_up_kernel(const float *__restrict__ x, const float *__restrict__ skip, const float *__restrict__ pred,
                                                                  long sb, long sc, long sy, long sx, float *__restrict__ out, int B, int h, int w, int C,
                                                                  int H, int W) {
     const int np = pred ? 1 : 0, Cp2 = (C >> 1) + np;
-    const long n = (long)B * H * W * Cp2;
     const float rh = (float)h / (float)H, rw = (float)w / (float)W;
-    for (long i = (long)blockIdx.x * kNetThreads + threadIdx.x; i < n; i += (long)gridDim.x * kNetThreads) {
-        const int c2 = (int)(i % Cp2);
-        const long pix = i / Cp2;
-        const int X = (int)(pix % W), Y = (int)((pix / W) % H);
-        const long b = pix / ((long)W * H);
-        const UpIdx uy = up_index(Y, rh, h), ux = up_index(X, rw, w);
-        float2 v[4];
-        if (c2 < np) {
-            const float *p = pred + b * sb;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long o = (long)((k >> 1) ? uy.i1 : uy.i0) * sy + (long)((k & 1) ? ux.i1 : ux.i0) * sx;
-                v[k] = make_float2(__ldg(p + o), __ldg(p + o + sc));
-            }
-        } else {
-            const int c = 2 * (c2 - np);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long o = ((b * h + ((k >> 1) ? uy.i1 : uy.i0)) * w + ((k & 1) ? ux.i1 : ux.i0)) * C + c;
-                v[k] = *reinterpret_cast<const float2 *>(x + o);
-                if (skip) { const float2 s2 = *reinterpret_cast<const float2 *>(skip + o); v[k].x += s2.x; v[k].y += s2.y; }
+    const int lane = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+        const int b = row / H, Y = row - b * H;
+        const UpIdx uy = up_index(Y, rh, h);
+        const float *x0 = x + ((long)b * h + uy.i0) * w * C, *x1 = x + ((long)b * h + uy.i1) * w * C;
+        const float *s0 = skip ? skip + ((long)b * h + uy.i0) * w * C : nullptr, *s1 = skip ? skip + ((long)b * h + uy.i1) * w * C : nullptr;
+        float *orow = out + (long)row * W * 2 * Cp2;
+        for (int X = pl; X < W; X += kNetThreads / 32) {
+            const UpIdx ux = up_index(X, rw, w);
+            float *o = orow + (long)X * 2 * Cp2 + 2 * np;
+            for (int c = 2 * lane; c < C; c += 64) {                 // C / 2 pairs: 32, 64, 128, 256 -- whole warps
+                const int a0 = ux.i0 * C + c, a1 = ux.i1 * C + c;
+                float2 v00 = *reinterpret_cast<const float2 *>(x0 + a0), v01 = *reinterpret_cast<const float2 *>(x0 + a1);
+                float2 v10 = *reinterpret_cast<const float2 *>(x1 + a0), v11 = *reinterpret_cast<const float2 *>(x1 + a1);
+                if (skip) {
+                    const float2 t00 = *reinterpret_cast<const float2 *>(s0 + a0), t01 = *reinterpret_cast<const float2 *>(s0 + a1);
+                    const float2 t10 = *reinterpret_cast<const float2 *>(s1 + a0), t11 = *reinterpret_cast<const float2 *>(s1 + a1);
+                    v00.x += t00.x; v00.y += t00.y; v01.x += t01.x; v01.y += t01.y; v10.x += t10.x; v10.y += t10.y; v11.x += t11.x; v11.y += t11.y;
+                }
+                // same association as ATen: l0h * (l0w * a + l1w * b) + l1h * (l0w * c + l1w * d)
+                float2 r;
+                r.x = uy.l0 * (ux.l0 * v00.x + ux.l1 * v01.x) + uy.l1 * (ux.l0 * v10.x + ux.l1 * v11.x);
+                r.y = uy.l0 * (ux.l0 * v00.y + ux.l1 * v01.y) + uy.l1 * (ux.l0 * v10.y + ux.l1 * v11.y);
+                *reinterpret_cast<float2 *>(o + c) = r;
             }
         }
-        float2 r;
-        r.x = uy.l0 * (ux.l0 * v[0].x + ux.l1 * v[1].x) + uy.l1 * (ux.l0 * v[2].x + ux.l1 * v[3].x);
-        r.y = uy.l0 * (ux.l0 * v[0].y + ux.l1 * v[1].y) + uy.l1 * (ux.l0 * v[2].y + ux.l1 * v[3].y);
-        *reinterpret_cast<float2 *>(out + 2 * i) = r;
+        if (np)                                                      // the two prediction channels in front: one thread per pixel
+            for (int X = threadIdx.x; X < W; X += kNetThreads) {
+                const UpIdx ux = up_index(X, rw, w);
+                const float *p = pred + b * sb;
+                const long o00 = uy.i0 * sy + ux.i0 * sx, o01 = uy.i0 * sy + ux.i1 * sx, o10 = uy.i1 * sy + ux.i0 * sx, o11 = uy.i1 * sy + ux.i1 * sx;
+                float2 r;
+                r.x = uy.l0 * (ux.l0 * __ldg(p + o00) + ux.l1 * __ldg(p + o01)) + uy.l1 * (ux.l0 * __ldg(p + o10) + ux.l1 * __ldg(p + o11));
+                r.y = uy.l0 * (ux.l0 * __ldg(p + o00 + sc) + ux.l1 * __ldg(p + o01 + sc)) + uy.l1 * (ux.l0 * __ldg(p + o10 + sc) + ux.l1 * __ldg(p + o11 + sc));
+                *reinterpret_cast<float2 *>(orow + (long)X * 2 * Cp2) = r;
+            }
     }
 }
+// Exactly x2 (H = 2h, W = 2w; every decoder stage): output pixels (2i+1, 2i+2) x (2j+1, 2j+2) interpolate the same four input
+// pixels (i, i+1) x (j, j+1), so one thread per input CELL (i, j in -1 .. size-1, clamped at the border) and channel pair loads
+// the taps once and writes up to four outputs: 2 loads per output instead of 8.  Weights come from up_index like the generic kernel.
+__global__ void __launch_bounds__(kNetThreads) decoder_up2_kernel(const float *__restrict__ x, const float *__restrict__ skip, const float *__restrict__ pred,
+                                                                  long sb, long sc, long sy, long sx, float *__restrict__ out, int B, int h, int w, int C) {
+    const int np = pred ? 1 : 0, Cp2 = (C >> 1) + np, Cp = 2 * Cp2, H = 2 * h, W = 2 * w;
+    const unsigned n_row = (unsigned)(w + 1) * (unsigned)Cp2;             // work items of one cell row
+    const int b = blockIdx.z, i = (int)blockIdx.y - 1;
+    const int r0 = max(i, 0), r1 = min(i + 1, h - 1);
+    for (unsigned k = blockIdx.x * kNetThreads + threadIdx.x; k < n_row; k += gridDim.x * kNetThreads) {
+        const int j = (int)(k / (unsigned)Cp2) - 1, c2 = (int)(k % (unsigned)Cp2);
+        const int q0 = max(j, 0), q1 = min(j + 1, w - 1);
+        float2 v00, v01, v10, v11;
+        if (c2 < np) {
+            const float *p = pred + b * sb;
+            const long o00 = r0 * sy + q0 * sx, o01 = r0 * sy + q1 * sx, o10 = r1 * sy + q0 * sx, o11 = r1 * sy + q1 * sx;
+            v00 = make_float2(__ldg(p + o00), __ldg(p + o00 + sc)); v01 = make_float2(__ldg(p + o01), __ldg(p + o01 + sc));
+            v10 = make_float2(__ldg(p + o10), __ldg(p + o10 + sc)); v11 = make_float2(__ldg(p + o11), __ldg(p + o11 + sc));
+        } else {
+            const int c = 2 * (c2 - np);
+            const long a00 = (((long)b * h + r0) * w + q0) * C + c, a01 = (((long)b * h + r0) * w + q1) * C + c;
+            const long a10 = (((long)b * h + r1) * w + q0) * C + c, a11 = (((long)b * h + r1) * w + q1) * C + c;
+            v00 = *reinterpret_cast<const float2 *>(x + a00); v01 = *reinterpret_cast<const float2 *>(x + a01);
+            v10 = *reinterpret_cast<const float2 *>(x + a10); v11 = *reinterpret_cast<const float2 *>(x + a11);
+            if (skip) {
+                const float2 t00 = *reinterpret_cast<const float2 *>(skip + a00), t01 = *reinterpret_cast<const float2 *>(skip + a01);
+                const float2 t10 = *reinterpret_cast<const float2 *>(skip + a10), t11 = *reinterpret_cast<const float2 *>(skip + a11);
+                v00.x += t00.x; v00.y += t00.y; v01.x += t01.x; v01.y += t01.y; v10.x += t10.x; v10.y += t10.y; v11.x += t11.x; v11.y += t11.y;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int Y = 2 * i + 1 + a;
+            if (Y < 0 || Y >= H) continue;
+            const UpIdx uy = up_index(Y, 0.5f, h);                        // rows (uy.i0, uy.i1) == (r0, r1) up to equal clamped rows
+            const float2 t0 = uy.i0 == r0 ? v00 : v10, t1 = uy.i0 == r0 ? v01 : v11;      // row i0
+            const float2 u0 = uy.i1 == r1 ? v10 : v00, u1 = uy.i1 == r1 ? v11 : v01;      // row i1
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int X = 2 * j + 1 + e;
+                if (X < 0 || X >= W) continue;
+                const UpIdx ux = up_index(X, 0.5f, w);
+                const bool l = ux.i0 == q0, rr = ux.i1 == q1;
+                const float2 a0 = l ? t0 : t1, a1 = rr ? t1 : t0, b0 = l ? u0 : u1, b1 = rr ? u1 : u0;
+                float2 r;
+                r.x = uy.l0 * (ux.l0 * a0.x + ux.l1 * a1.x) + uy.l1 * (ux.l0 * b0.x + ux.l1 * b1.x);
+                r.y = uy.l0 * (ux.l0 * a0.y + ux.l1 * a1.y) + uy.l1 * (ux.l0 * b0.y + ux.l1 * b1.y);
+                *reinterpret_cast<float2 *>(out + (((long)b * H + Y) * W + X) * Cp + 2 * c2) = r;
+            }
+        }
+    }
+}
+
 // adjoint (deterministic gather): one thread per low-resolution pixel and channel pair; the 1-D weights of the candidate output
 // rows / columns are derived once, then the non-zero ones are walked.  gx receives the gradient of x and of skip alike.
 constexpr int kUpWin = 8;          // candidate output rows per input row: 2 * scale + 3 <= 8 covers scale factors up to 2.5
@@ -355,6 +418,16 @@ __global__ void __launch_bounds__(kNetThreads) decoder_up_bwd_kernel(const float
         } else {
             *reinterpret_cast<float2 *>(gx + ((b * h + i) * w + j) * C + 2 * (c2 - np)) = acc;
         }
+    }
+}
+
+__global__ void __launch_bounds__(kNetThreads) scale_copy_strided_kernel(const float *__restrict__ g, float scale, float *__restrict__ out, long sb, long sc, long sy,
+                                                                         long sx, int B, int h, int w) {
+    const long n = (long)B * 2 * h * w;
+    for (long i = (long)blockIdx.x * kNetThreads + threadIdx.x; i < n; i += (long)gridDim.x * kNetThreads) {
+        const int j = (int)(i % w), r = (int)((i / w) % h);
+        const long bc = i / ((long)w * h);
+        out[(bc >> 1) * sb + (bc & 1) * sc + r * sy + j * sx] = g[i] * scale;
     }
 }
 
@@ -433,6 +506,11 @@ extern "C" int tef_upsample_scale(const float *pred, const long *strides, int h,
 extern "C" int tef_upsample_scale_bwd(const float *gout, int B, int H, int W, float scale, float *gpred, const long *strides, int h, int w, void *stream) {
     if (!gout || !gpred || !strides || B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return TEF_EINVAL;
     const long n = (long)B * 2 * h * w;
+    if (h == H && w == W) {                                 // identity-sized head: source index == output index, weights (1, 0)
+        ProfScope ps(K_NETWORK, (cudaStream_t)stream);
+        scale_copy_strided_kernel<<<grid_for(n), kNetThreads, 0, (cudaStream_t)stream>>>(gout, scale, gpred, strides[0], strides[1], strides[2], strides[3], B, h, w);
+        return (int)cudaGetLastError();
+    }
     const float win = ((float)H / (float)h * 2.0f + 3.0f) * ((float)W / (float)w * 2.0f + 3.0f);      // output pixels an element looks at
     const int lpe = win <= 40.0f ? 1 : (win <= 160.0f ? 8 : 32);
     const unsigned nb = (unsigned)((n * lpe + kNetThreads - 1) / kNetThreads);
@@ -449,8 +527,13 @@ extern "C" int tef_decoder_up(const float *x, const float *skip, const float *pr
     const long z[4] = { 0, 0, 0, 0 };
     const long *ps = pred ? pred_strides : z;
     ProfScope ps_(K_NETWORK, (cudaStream_t)stream);
-    decoder_up_kernel<<<grid_for((long)B * H * W * ((C >> 1) + (pred ? 1 : 0))), kNetThreads, 0, (cudaStream_t)stream>>>(x, skip, pred, ps[0], ps[1], ps[2], ps[3],
-                                                                                                                     out, B, h, w, C, H, W);
+    if (H == 2 * h && W == 2 * w && B <= 65535 && h + 1 <= 65535) {
+        const unsigned n_row = (unsigned)(w + 1) * (unsigned)((C >> 1) + (pred ? 1 : 0));
+        decoder_up2_kernel<<<dim3((n_row + kNetThreads - 1) / kNetThreads, h + 1, B), kNetThreads, 0, (cudaStream_t)stream>>>(x, skip, pred, ps[0], ps[1], ps[2],
+                                                                                                                        ps[3], out, B, h, w, C);
+    } else {
+        decoder_up_kernel<<<B * H, kNetThreads, 0, (cudaStream_t)stream>>>(x, skip, pred, ps[0], ps[1], ps[2], ps[3], out, B, h, w, C, H, W);
+    }
     return (int)cudaGetLastError();
 }
 extern "C" int tef_decoder_up_bwd(const float *gout, float *gx, float *gpred, const long *pred_strides, int B, int h, int w, int C, int H, int W,

@@ -99,24 +99,26 @@ def test_upsample_scale_matches_interpolate(h, w, H, W, channels_last):
         assert rel(a, b) < TOL
 
 
-@pytest.mark.parametrize("B,C,h,w,with_pred,with_skip", [(2, 8, 6, 9, True, True), (1, 64, 16, 16, True, True), (2, 512, 4, 4, False, True), (2, 32, 5, 3, True, False)])
-def test_decoder_up_matches_add_cat_interpolate(B, C, h, w, with_pred, with_skip):
+@pytest.mark.parametrize("scale", [2, 1])        # 2: the cell-wise x2 kernel every decoder stage uses; 1: the generic kernel
+@pytest.mark.parametrize("B,C,h,w,with_pred,with_skip", [(2, 8, 6, 9, True, True), (1, 64, 16, 16, True, True), (2, 512, 4, 4, False, True), (2, 32, 5, 3, True, False),
+                                                         (1, 6, 1, 1, True, True)])
+def test_decoder_up_matches_add_cat_interpolate(B, C, h, w, with_pred, with_skip, scale):
     from taming_event_flow_b200 import netops
 
     torch.manual_seed(C)
     cl = lambda t: t.contiguous(memory_format=torch.channels_last)
     x0, s0, p0 = cl(torch.randn(B, C, h, w, device="cuda")), cl(torch.randn(B, C, h, w, device="cuda")), cl(torch.randn(B, 2, h, w, device="cuda"))
-    g = torch.randn(B, C + (2 if with_pred else 0), 2 * h, 2 * w, device="cuda")
+    g = torch.randn(B, C + (2 if with_pred else 0), scale * h, scale * w, device="cuda")
     out = {}
     for fused in (False, True):
         x, sk, pr = x0.clone().requires_grad_(True), s0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
         if fused:
-            y = netops.decoder_up(x, sk if with_skip else None, pr if with_pred else None, 2)
+            y = netops.decoder_up(x, sk if with_skip else None, pr if with_pred else None, scale)
         else:
             y = x + sk if with_skip else x
             if with_pred:
                 y = torch.cat([pr, y], 1)
-            y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=False)
+            y = F.interpolate(y, scale_factor=scale, mode="bilinear", align_corners=False)
         (y * g).sum().backward()
         out[fused] = [y, x.grad] + ([sk.grad] if with_skip else []) + ([pr.grad] if with_pred else [])
     for a, b in zip(out[True], out[False]):
