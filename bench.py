@@ -816,15 +816,17 @@ def run_train(args, wl, quiet=False):
     cfg = syn.loss_config(wl["H"], wl["W"], B_local, P, wl["S"], wl["mode"], warping=wl["warping"])
     loss_fn = getattr(tef_flow, wl["warping"])(cfg, dev)
     torch.manual_seed(0)
-    # The network stays on PyTorch/cuDNN (north_star).  What is applied to it: channels_last, optional bf16
-    # autocast (the CM loss stays fp32), one CUDA graph over forward + loss + backward, a flat gradient buffer with a bucketed
-    # SUM all-reduce issued under the backward pass, fused Adam.
+    # The network's convolutions stay on PyTorch/cuDNN (north_star).  What is applied around them: channels_last,
+    # the element-wise stages as fused CUDA kernels with one weight gradient per layer and loss window (netops, csrc/tef_net.cu),
+    # one CUDA graph over forward + loss + backward, a flat gradient buffer with a bucketed SUM all-reduce issued under the
+    # backward pass, fused Adam; optional bf16 autocast (plain modules; the CM loss stays fp32).
     mode = getattr(args, "train_mode", None) or os.environ.get("TEF_TRAIN_MODE", TRAIN_MODE_DEFAULT)
     dtype = getattr(args, "train_dtype", None) or os.environ.get("TEF_TRAIN_DTYPE", TRAIN_DTYPE_DEFAULT)
     autocast = torch.bfloat16 if dtype == "bf16" else None
     torch.backends.cudnn.benchmark = True
     fp32_heads = os.environ.get("TEF_TRAIN_FP32_HEADS", "1") != "0" and getattr(args, "fp32_heads", True)
-    model = RecEVFlowNet(num_bins=2, fp32_heads=fp32_heads).to(dev).to(memory_format=torch.channels_last)
+    fused = os.environ.get("TEF_TRAIN_FUSED", "1") != "0"          # 0: the plain PyTorch modules (A/B of the fused element-wise kernels)
+    model = RecEVFlowNet(num_bins=2, fp32_heads=fp32_heads, fused=fused).to(dev).to(memory_format=torch.channels_last)
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)      # the optimizer step stays outside the captured graph
     reducer = GradReducer(list(model.parameters()), world)
     from taming_event_flow_b200.dataloader.encodings import events_to_channels_batched
@@ -879,7 +881,7 @@ def run_train(args, wl, quiet=False):
     res = {"metric": "train_throughput", "value": B_global * P * args.steps / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (PyTorch/cuDNN, channels_last, %s, 31.4M params)" % (("bf16 autocast, %s flow heads, fp32 CM loss" % ("fp32" if fp32_heads else "bf16")) if autocast else "fp32/TF32"),
+           "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (cuDNN convolutions, channels_last, %s, 31.4M params)" % (("bf16 autocast on the plain PyTorch modules (the fused element-wise kernels are fp32), %s flow heads, fp32 CM loss" % ("fp32" if fp32_heads else "bf16")) if autocast else "fp32/TF32, plain PyTorch modules" if not fused else "fp32/TF32; ConvGRU gates, bias + activation, decoder inputs and flow-head up-sampling as fused CUDA kernels (netops), one weight gradient per layer and loss window"),
                           step_mode=(("one CUDA graph over forward + CM loss + backward%s; clip, Adam eager" % (" + the bucketed all-reduces" if graphed.comm_captured else "; all-reduce after the replay"))
                                      if mode == "graph" else "eager"),
                           optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets) under the backward pass" % len(reducer.buckets)),
