@@ -568,7 +568,7 @@ def run_ours(args, wl):
     d2h = h_grads.numel() * 4 + 4
     copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 40))          # the same K steps as the resident loop (the first one pays its un-overlapped upload)
 
     def run_pipeline(host_tensors, windows_of, full):
         """host_tensors: pinned inputs of one step; windows_of(slot, t) -> the four event tensors of pass t.
