@@ -72,7 +72,7 @@ typedef struct tef_cm_desc {
     float *loss;           /* [1] scalar loss                                          */
     const float *grad_out; /* [1] upstream gradient of the loss (backward)             */
     /* workspace written by the forward call and read by the backward call (sizes from tef_cm_sizes) */
-    void *sort_bins;       /* int [nbins + 1]  tile-sort histogram / offsets           */
+    void *sort_bins;       /* int [nbins + 1]  tile-sort histogram / offsets (16-byte aligned) */
     void *sort_sums;       /* int scan scratch                                         */
     void *sorted_ev;       /* 32-byte records [rows]: (ts, y, x, sample index bits, mask+, mask-, 0, 0), tile-sorted */
     void *posbuf;          /* float2 [F][P+1][rows_grad] chain positions (x, y) (Iterative) */

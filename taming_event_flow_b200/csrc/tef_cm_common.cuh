@@ -28,7 +28,7 @@ struct SortGeom {
     int B, H, W, tiles_x, tiles;     // 16x8-pixel tiles per sample
     long nbins;                      // nseg * B * tiles * kBinsPerTile
     int *bins;                       // [nbins + 1] histogram -> offsets -> bin ends
-    int *sums;                       // scan scratch, one int per 2048 bins
+    int *sums;                       // scan scratch, one int per scan chunk (4096 bins; sized for 2048 by tef_cm_workspace)
     float4 *rec;                     // sorted rows, 32 B each: (ts, y, x, sample index bits | mask+, mask-, 0, 0)
 };
 
