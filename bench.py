@@ -849,7 +849,7 @@ def run_train(args, wl, quiet=False):
         # static inputs of the captured step; a step's events are copied in before the replay (inside the timed region)
         static = [(src[t][0].clone(), masks[t][0], src[t][1].clone(), masks[t][1]) for t in range(P)]
         graphed = GraphedTrainStep(model, loss_fn, opt, static, flow_scaling=32.0, clip_grad=100.0, encode=encode, reducer=reducer, autocast=autocast,
-                                   capture_collectives=os.environ.get("TEF_TRAIN_CAPTURE_NCCL", "0") == "1")
+                                   capture_collectives=False)       # capturing the all-reduces in the graph hung at 8 GPUs with the final build: not offered here
 
         def step(i):
             for t in range(P):

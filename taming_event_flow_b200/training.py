@@ -215,7 +215,8 @@ class GraphedTrainStep:
         # the recurrent states become static tensors: read at the start of every replay, written back at its end
         self.states = [s.detach().clone() for s in model.states]
         self.graph = torch.cuda.CUDAGraph()
-        # capture_collectives: the bucketed all-reduces the gradient hooks issue (on NCCL's stream, forked from the capturing
+        # capture_collectives (EXPERIMENTAL, off everywhere: with the fused network step a run at 8 GPUs never finished its first
+        # replay -- gpurun call 148 of round 2 -- and it has not been debugged since): the bucketed all-reduces the gradient hooks issue (on NCCL's stream, forked from the capturing
         # stream) become branches of the graph and overlap the tail of the captured backward pass; otherwise they are issued
         # after the replay
         self.comm_captured = bool(capture_collectives and self.reducer.world_size > 1)
