@@ -115,6 +115,11 @@ class RecEVFlowNet(nn.Module):
     def forward(self, x, flow_scaling=1.0):
         """`flow_scaling`: extra factor folded into the flow maps (upstream multiplies the network output by
         config["loss"]["flow_scaling"] in the training loop, train_flow.py:106-108)."""
+        # upstream pads the input on the top / left to a multiple of 16 and crops the flow maps again (models/model_util.py:29-71,
+        # models/model.py:66-85); a no-op for the benchmark resolutions
+        ph, pw = (16 - x.shape[2] % 16) % 16, (16 - x.shape[3] % 16) % 16
+        if ph or pw:
+            x = F.pad(x, (pw, 0, ph, 0))
         H, W = x.shape[2], x.shape[3]
         skips = []
         for i in range(self.num_encoders):
@@ -144,7 +149,7 @@ class RecEVFlowNet(nn.Module):
                 x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
             x = self._conv_act(self.dec[i], x, slot=slot)
             pred, flow = self._head(i, x, (H, W), float(2 ** (self.num_encoders - 1 - i)) * float(flow_scaling))
-            flows.append(flow)
+            flows.append(flow[..., ph:, pw:].contiguous() if (ph or pw) else flow)
         return {"flow": flows}
 
 
@@ -154,3 +159,47 @@ def _default_conv(c):
 
 def count_parameters(m):
     return sum(p.numel() for p in m.parameters())
+
+
+def from_upstream_state_dict(sd):
+    """State dict of upstream's ``RecEVFlowNet`` (``models/model.py``; keys ``arch.encoders.i.conv.conv2d.*``,
+    ``arch.encoders.i.recurrent_block.{update,reset,out}_gate.*``, ``arch.resblocks.j.conv{1,2}.*``, ``arch.decoders.i.conv2d.*``,
+    ``arch.preds.i.conv2d.*``) -> the names of this module, so that a checkpoint trained with the reference loads into
+    ``RecEVFlowNet.load_state_dict``.  The update and the reset gate are stacked into ``gate_zr`` (update first)."""
+    out = {}
+    n_enc = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("arch.encoders."))
+    n_res = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("arch.resblocks."))
+    for i in range(n_enc):
+        for wb in ("weight", "bias"):
+            out["enc_conv.%d.%s" % (i, wb)] = sd["arch.encoders.%d.conv.conv2d.%s" % (i, wb)]
+            g = "arch.encoders.%d.recurrent_block." % i
+            out["enc_gru.%d.gate_zr.%s" % (i, wb)] = torch.cat([sd[g + "update_gate." + wb], sd[g + "reset_gate." + wb]], 0)
+            out["enc_gru.%d.gate_c.%s" % (i, wb)] = sd[g + "out_gate." + wb]
+            out["dec.%d.%s" % (i, wb)] = sd["arch.decoders.%d.conv2d.%s" % (i, wb)]
+            out["heads.%d.%s" % (i, wb)] = sd["arch.preds.%d.conv2d.%s" % (i, wb)]
+    for j in range(n_res):
+        for wb in ("weight", "bias"):
+            out["res.%d.0.%s" % (j, wb)] = sd["arch.resblocks.%d.conv1.%s" % (j, wb)]
+            out["res.%d.1.%s" % (j, wb)] = sd["arch.resblocks.%d.conv2.%s" % (j, wb)]
+    return out
+
+
+def to_upstream_state_dict(sd):
+    """The inverse of ``from_upstream_state_dict``: this module's state dict under upstream's parameter names."""
+    out = {}
+    n_enc = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("enc_conv."))
+    n_res = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("res."))
+    for i in range(n_enc):
+        for wb in ("weight", "bias"):
+            out["arch.encoders.%d.conv.conv2d.%s" % (i, wb)] = sd["enc_conv.%d.%s" % (i, wb)]
+            zr = sd["enc_gru.%d.gate_zr.%s" % (i, wb)]
+            g = "arch.encoders.%d.recurrent_block." % i
+            out[g + "update_gate." + wb], out[g + "reset_gate." + wb] = zr[:zr.shape[0] // 2], zr[zr.shape[0] // 2:]
+            out[g + "out_gate." + wb] = sd["enc_gru.%d.gate_c.%s" % (i, wb)]
+            out["arch.decoders.%d.conv2d.%s" % (i, wb)] = sd["dec.%d.%s" % (i, wb)]
+            out["arch.preds.%d.conv2d.%s" % (i, wb)] = sd["heads.%d.%s" % (i, wb)]
+    for j in range(n_res):
+        for wb in ("weight", "bias"):
+            out["arch.resblocks.%d.conv1.%s" % (j, wb)] = sd["res.%d.0.%s" % (j, wb)]
+            out["arch.resblocks.%d.conv2.%s" % (j, wb)] = sd["res.%d.1.%s" % (j, wb)]
+    return out

@@ -171,7 +171,6 @@ class _FusedConvGRU(torch.autograd.Function):
             n = stacks.used * B
             gw_c = _conv_bwd_weight(stacks.g["c"][:n], stacks.x["xrh"][:n], w_c, 1, pad)
             gw_zr = _conv_bwd_weight(stacks.g["zr"][:n], stacks.x["xh"][:n], w_zr, 1, pad)
-        ctx.t = None
         return gx, gh, gw_zr, (gb_zr if has_bzr else None), gw_c, (gb_c if has_bc else None), None, None
 
 
@@ -232,7 +231,6 @@ class _ConvBiasAct(torch.autograd.Function):
             if slot == 0:
                 n = stacks.used * B
                 gw = _conv_bwd_weight(stacks.g["y"][:n], stacks.x["x"][:n], w, stride, padding)
-        ctx.t = None
         # the residual's gradient must not alias a stack slot the next window overwrites while autograd may still hold it
         return gx, gw, gb, ((gpre.clone() if slot is not None else gpre) if has_res else None), None, None, None, None, None
 
