@@ -137,7 +137,10 @@ class _FusedConvGRU(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
+        if ctx.t is None:
+            raise RuntimeError("a fused network operator can be back-propagated once (its activations are released by the first backward pass)")
         xh, xrh, zr, cand, w_zr, w_c = ctx.t
+        ctx.t = None
         M, B, Cx, C, pad, has_bzr, has_bc, stacks, slot = ctx.dims
         L = _lib.lib()
         st = _lib.stream()
@@ -209,7 +212,10 @@ class _ConvBiasAct(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
+        if ctx.t is None:
+            raise RuntimeError("a fused network operator can be back-propagated once (its activations are released by the first backward pass)")
         x, w, y = ctx.t
+        ctx.t = None
         act, stride, padding, has_b, has_res, M, C, B, stacks, slot = ctx.cfg
         L = _lib.lib()
         gy = _cl(gy)
