@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(kNetThreads) upsample_scale_bwd_kernel(const f
 // ---- decoder stage input (models/arch.py decoder loop): (x + skip), the previous flow prediction concatenated in front, and the
 // bilinear x2 up-sampling that precedes the decoder's convolution -- one kernel instead of add, cat and up-sample ----------------
 // x, skip: [B][h][w][C] (NHWC);  pred: [B][2][h][w] through element strides, or NULL;  out: [B][H][W][Cp], Cp = C + (pred ? 2 : 0).
-// One thread per output pixel and channel PAIR (C is even; Cp = 66, 130, 258 are not multiples of four).
-// One CTA per output row (b, Y): 32 lanes walk the channel pairs of a pixel (coalesced 256-byte runs), 8 pixel lanes walk
-// the row -- no integer division anywhere (the flat-index version spent its time in 64-bit div / mod).
+// Channels travel in PAIRS (C is even; Cp = 66, 130, 258 are not multiples of four).  Generic scale: one CTA per output row
+// (b, Y), 32 lanes over the channel pairs of a pixel (coalesced 256-byte runs), 8 pixel lanes along the row, the two prediction
+// channels by one thread per pixel.  Every decoder stage is exactly x2 and takes decoder_up2_kernel below instead.
 __global__ void __launch_bounds__(kNetThreads) decoder_up_kernel(const float *__restrict__ x, const float *__restrict__ skip, const float *__restrict__ pred,
                                                                  long sb, long sc, long sy, long sx, float *__restrict__ out, int B, int h, int w, int C,
                                                                  int H, int W) {

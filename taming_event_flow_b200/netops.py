@@ -339,4 +339,6 @@ def decoder_up(x, skip=None, pred=None, scale=2, out=None):
     _lib.require_cuda(x, skip, pred)
     if pred is not None and (pred.dim() != 4 or pred.shape[1] != 2 or any(st <= 0 for st in pred.stride())):
         raise _lib.TefShapeError("decoder_up expects a dense [B, 2, h, w] flow prediction")
+    if not (1 <= scale <= 2.5):
+        raise _lib.TefError("decoder_up supports scale factors 1 .. 2.5 (the adjoint kernel's window), got %r" % (scale,))
     return _DecoderUp.apply(x, skip, pred, scale, [out] if out is not None else None)
