@@ -682,4 +682,4 @@ def test_graphed_train_step_follows_the_eager_step():
     assert all(np.isfinite(out["eager"]))
     assert abs(out["eager"][3] - out["eager"][2]) > 1e-3 * abs(out["eager"][2]), out["eager"]          # the carried states do matter
     for a, b in zip(out["eager"][2:], out["graph"][2:]):
-        assert abs(a - b) <= 2e-4 * abs(a), (out["eager"], out["graph"])
+        assert abs(a - b) <= 5e-4 * abs(a), (out["eager"], out["graph"])
