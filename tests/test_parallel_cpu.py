@@ -120,3 +120,52 @@ def test_grad_reducer_overlapped_buckets_match_single_process(tmp_path):
         assert r["nbytes"] == sum(p.numel() * 4 for p in model.parameters())
         assert r["views"] and r["strides"] and r["buckets"] >= 2
         assert r["in_backward"] == r["buckets"]            # every bucket was issued from a hook, before backward() returned
+
+
+def _net_window_loss(net, xs):
+    """Stand-in for the CM loss over a recurrent window: a SUM over samples of a per-sample quantity of every pass's flow maps."""
+    net.reset_states()
+    net.begin_window(len(xs))
+    loss = 0.0
+    for x in xs:
+        for f in net(x, flow_scaling=32.0)["flow"]:
+            loss = loss + (f ** 2).flatten(1).mean(1).sum()
+    return loss
+
+
+def _net_worker(rank, world, port, gb, out):
+    from taming_event_flow_b200.flownet import RecEVFlowNet
+    from taming_event_flow_b200.training import GradReducer
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(5)
+    net = RecEVFlowNet(num_bins=2, base_channels=4)
+    xs = [torch.rand(gb, 2, 32, 32) for _ in range(2)]
+    a, b = shard_range(gb, world, rank)
+    red = GradReducer(list(net.parameters()), world, bucket_bytes=4096)
+    red.zero()
+    _net_window_loss(net, [x[a:b] for x in xs]).backward()
+    red.finish()
+    if rank == 0:
+        torch.save([p.grad.clone() for p in net.parameters()], out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_recurrent_window_matches_the_global_batch(tmp_path):
+    """The recurrent network over a two-pass window (back-propagation through time, states per shard), batch sharded over two
+    ranks, SUM all-reduce from the flat gradient buffer: equals one process on the global batch."""
+    from taming_event_flow_b200.flownet import RecEVFlowNet
+
+    gb, world = 4, 2
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_net_worker, args=(world, _free_port(), gb, out), nprocs=world, join=True)
+    got = torch.load(out)
+    torch.manual_seed(5)
+    net = RecEVFlowNet(num_bins=2, base_channels=4)
+    xs = [torch.rand(gb, 2, 32, 32) for _ in range(2)]
+    _net_window_loss(net, xs).backward()
+    for g, p in zip(got, net.parameters()):
+        assert torch.allclose(g, p.grad, rtol=1e-4, atol=1e-6)
