@@ -108,7 +108,7 @@ class RecEVFlowNet(nn.Module):
                 pred = torch.tanh(self.heads[i](x.float()))
                 return pred, F.interpolate(pred, size=size, mode="bilinear", align_corners=False) * scale
         pred = torch.tanh(self.heads[i](x))
-        if self.fused and pred.is_cuda and pred.dtype == torch.float32 and not torch.is_autocast_enabled("cuda"):
+        if self.fused and netops.usable_input(pred):
             return pred, netops.upsample_scale(pred, size, scale)
         return pred, F.interpolate(pred, size=size, mode="bilinear", align_corners=False) * scale
 
