@@ -11,8 +11,6 @@ if [ "$N" = "1" ]; then
 fi
 timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2n_bench_n$N.json 2>> gpurun_out/r2n.err; tail -c 700 gpurun_out/r2n_bench_n$N.json; echo
 timeout 600 $TR bench.py --gpus $N --workload train_128x128_gb64 --steps 6 > gpurun_out/r2n_train_gb64_n$N.json 2>> gpurun_out/r2n.err; cut -c1-260 gpurun_out/r2n_train_gb64_n$N.json
-if [ "$N" != "1" ]; then
-  TEF_TRAIN_CAPTURE_NCCL=1 timeout 600 $TR bench.py --gpus $N --workload train_128x128_gb64 --steps 6 > gpurun_out/r2n_train_gb64_capnccl_n$N.json 2>> gpurun_out/r2n.err; cut -c1-260 gpurun_out/r2n_train_gb64_capnccl_n$N.json
-  TEF_TRAIN_CAPTURE_NCCL=1 timeout 600 $TR bench.py --gpus $N --workload train_128x128_b8 --steps 6 > gpurun_out/r2n_train_b8_capnccl_n$N.json 2>> gpurun_out/r2n.err; cut -c1-260 gpurun_out/r2n_train_b8_capnccl_n$N.json
-fi
+# (the two TEF_TRAIN_CAPTURE_NCCL=1 runs that followed here never finished their first replay at 8 GPUs and ran into the call's time
+#  limit -- 1 023 s x 8 GPUs, the rest of the round's GPU budget; the switch has been removed from bench.py)
 tail -5 gpurun_out/r2n.err
