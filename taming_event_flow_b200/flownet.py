@@ -81,10 +81,15 @@ class RecEVFlowNet(nn.Module):
         """Open a loss window of `passes` forward calls whose loss back-propagates through all of them (upstream's training loop,
         train_flow.py:106-137): the recurrent layers then compute their weight gradients once per window instead of once per
         pass (netops.WindowStacks).  `passes` = 0 switches back to per-pass gradients."""
-        for cell in self.enc_gru:
-            cell.stacks.begin(passes if self.fused else 0)
-        for st in self._stacks.values():
-            st.begin(passes if self.fused else 0)
+        lost = None
+        for st in [cell.stacks for cell in self.enc_gru] + list(self._stacks.values()):
+            try:
+                st.begin(passes if self.fused else 0)
+            except RuntimeError as exc:          # the window before lost a layer's weight gradient: re-arm every layer, then report
+                lost = lost or exc
+                st.begin(passes if self.fused else 0)
+        if lost is not None:
+            raise lost
 
     def reset_states(self):
         self.states = [None] * self.num_encoders

@@ -72,15 +72,36 @@ class WindowStacks:
     operators keep the convolution inputs and the output gradients of all passes side by side -- `x[name]` and `g[name]` are
     [P*B, C, H, W] channels_last stacks, pass t in rows t*B..(t+1)*B, written in place by the kernels that produce them -- and
     the backward of the window's FIRST pass (the last to run) computes ONE weight gradient over all of them.
-    Requires the loss to back-propagate through every pass down to the first, which is what upstream's training loop does
-    (``train_flow.py:106-137``); `begin(P)` opts a window in, a layer called more often than P times falls back to the
-    per-pass gradient."""
+    Requires the loss to back-propagate through the window's first pass, which is what upstream's training loop does
+    (``train_flow.py:106-137``: every pass feeds the loss); `begin(P)` opts a window in, a layer called more often than P times
+    falls back to the per-pass gradient.  Passes whose backward never ran (their output did not reach the loss) contribute zero:
+    their rows of the gradient stacks are cleared before the window's gradient is formed.  If backward ran for later passes but
+    never for the first one, the window's weight gradient was never emitted; the next `begin` raises instead of training on."""
 
     def __init__(self):
         self.P, self.slot, self.used, self.key, self.x, self.g = 0, 0, 0, None, {}, {}
+        self.ran = set()          # slots whose backward has run in this window
 
     def begin(self, P):
+        if self.ran and 0 not in self.ran:
+            ran, self.ran = sorted(self.ran), set()
+            raise RuntimeError("deferred weight gradient lost: the previous loss window back-propagated through passes %s of a layer but not "
+                               "through its first pass, whose backward emits the window's weight gradient (netops.WindowStacks); "
+                               "open the window with begin_window(0) for losses that skip the first pass" % ran)
         self.P, self.slot, self.used = int(P), 0, 0
+        self.ran = set()
+
+    def window_rows(self, slot, B):
+        """Called by the backward of pass `slot`: records it; for the first pass (the one that emits the window's weight gradient)
+        clears the gradient rows of passes whose backward never ran and returns the number of rows to reduce over, else None."""
+        self.ran.add(slot)
+        if slot != 0:
+            return None
+        for t in range(self.used):
+            if t not in self.ran:
+                for g in self.g.values():
+                    self.rows(g, t, B).zero_()
+        return self.used * B
 
     def take_slot(self):
         """Slot of this forward call, or None when the window is not open / already full / gradients are off."""
@@ -170,8 +191,8 @@ class _FusedConvGRU(torch.autograd.Function):
         gxh = _cl(gxh)
         gx = torch.empty((B, Cx, xh.shape[2], xh.shape[3]), dtype=torch.float32, device=gout.device, memory_format=CL)
         _lib.check(L.tef_gru_input_grads(_lib.ptr(gxrh), _lib.ptr(gxh), _lib.ptr(gx), _lib.ptr(gh), ctypes.c_long(M), Cx, C, st), "tef_gru_input_grads")
-        if slot == 0:                                           # the window's first pass: every pair of the window is in the stacks
-            n = stacks.used * B
+        n = stacks.window_rows(slot, B) if slot is not None else None
+        if n is not None:                                       # the window's first pass: every pair of the window is in the stacks
             gw_c = _conv_bwd_weight(stacks.g["c"][:n], stacks.x["xrh"][:n], w_c, 1, pad)
             gw_zr = _conv_bwd_weight(stacks.g["zr"][:n], stacks.x["xh"][:n], w_zr, 1, pad)
         return gx, gh, gw_zr, (gb_zr if has_bzr else None), gw_c, (gb_c if has_bc else None), None, None
@@ -234,8 +255,8 @@ class _ConvBiasAct(torch.autograd.Function):
         else:
             if ctx.needs_input_grad[0]:
                 gx = _conv_bwd_input(gpre, x, w, stride, padding)
-            if slot == 0:
-                n = stacks.used * B
+            n = stacks.window_rows(slot, B)
+            if n is not None:
                 gw = _conv_bwd_weight(stacks.g["y"][:n], stacks.x["x"][:n], w, stride, padding)
         # the residual's gradient must not alias a stack slot the next window overwrites while autograd may still hold it
         return gx, gw, gb, ((gpre.clone() if slot is not None else gpre) if has_res else None), None, None, None, None, None

@@ -232,3 +232,50 @@ def test_a_fused_operator_back_propagates_once(emulated):
 def test_decoder_up_rejects_scales_its_adjoint_cannot_take(emulated):
     with pytest.raises(_lib.TefError):
         netops.decoder_up(torch.zeros(1, 4, 4, 4), None, None, 4)
+
+
+def _window_grads(net, xs, use, window):
+    """Gradients of a loss that only looks at the flow maps of the passes in `use`."""
+    net.reset_states()
+    net.zero_grad(set_to_none=True)
+    net.begin_window(window)
+    loss = 0.0
+    for t, x in enumerate(xs):
+        fl = net(x)["flow"]
+        if t in use:
+            loss = loss + sum((f ** 2).sum() for f in fl)
+    loss.backward()
+    return [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+
+
+def _set_fused(net, fused):
+    net.fused = fused
+    for c in net.enc_gru:
+        c.fused = fused
+
+
+def test_passes_that_do_not_reach_the_loss_contribute_zero_to_the_window_gradient(emulated):
+    """The decoder of a pass the loss ignores never runs its backward: its rows of the gradient stacks (stale from the window before)
+    must not leak into the deferred weight gradient."""
+    torch.manual_seed(2)
+    net = RecEVFlowNet(num_bins=2, base_channels=4)
+    xs = [torch.rand(1, 2, 32, 32) for _ in range(3)]
+    _set_fused(net, True)
+    _window_grads(net, xs, {0, 1, 2}, 3)                      # fills every slot of the gradient stacks
+    got = _window_grads(net, xs, {0, 2}, 3)                   # the middle pass reaches the loss through the recurrent states only
+    _set_fused(net, False)
+    want = _window_grads(net, xs, {0, 2}, 0)
+    assert max(rel(a, b) for a, b in zip(got, want)) < 2e-5
+
+
+def test_a_window_whose_first_pass_never_back_propagates_is_reported(emulated):
+    torch.manual_seed(3)
+    net = RecEVFlowNet(num_bins=2, base_channels=4)
+    xs = [torch.rand(1, 2, 32, 32) for _ in range(2)]
+    _set_fused(net, True)
+    _window_grads(net, xs, {1}, 2)                            # decoders and heads of pass 0 never run their backward
+    with pytest.raises(RuntimeError, match="deferred weight gradient lost"):
+        net.begin_window(2)
+    net.begin_window(2)                                       # reported once; the next window starts clean
+    _window_grads(net, xs, {0, 1}, 2)
+    net.begin_window(0)
