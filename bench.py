@@ -890,7 +890,7 @@ def run_train(args, wl, quiet=False):
            "config": dict(workload_config(wl), batch_global=B_global, batch_per_gpu=B_local, network="RecEVFlowNet (cuDNN convolutions, channels_last, %s, 31.4M params)" % (("bf16 autocast on the plain PyTorch modules (the fused element-wise kernels are fp32), %s flow heads, fp32 CM loss" % ("fp32" if fp32_heads else "bf16")) if autocast else "fp32/TF32, plain PyTorch modules" if not fused else "fp32/TF32; ConvGRU gates, bias + activation, decoder inputs and flow-head up-sampling as fused CUDA kernels (netops), one weight gradient per layer and loss window"),
                           step_mode=(("one CUDA graph over forward + CM loss + backward%s; clip, Adam eager" % (" + the bucketed all-reduces" if graphed.comm_captured else "; all-reduce after the replay"))
                                      if mode == "graph" else "eager"),
-                          optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets) under the backward pass" % len(reducer.buckets)),
+                          optimizer="fused Adam lr 1e-5, clip 100, flat gradient buffer, bucketed SUM all-reduce (%d buckets; issued from gradient hooks in eager mode, after the replay in graph mode)" % len(reducer.buckets)),
            "loss": float(loss.item()), "events_per_step": B_global * P * (wl["N"] + wl["Nd"])}
     if own_pg:
         dist.barrier()
